@@ -1,0 +1,389 @@
+// k_constraints.cuh -- alignment -> subexon bit-vector constraints for one (sample, component).
+//
+// Replaces Constraints::BuildConstraints and its helpers:
+//   read -> component assignment   Constraints.cpp:259-283  (closed form, see group_ranges)
+//   ConvertAlignmentToBitTable     Constraints.cpp:4-72
+//   clip rule                      Constraints.cpp:310-326
+//   MateReadIds (mate join)        Constraints.hpp:52-231, Constraints.cpp:333-372
+//   CoalesceSameConstraints        Constraints.cpp:74-150
+//   ComputeNormAbund               Constraints.cpp:152-238
+#pragma once
+#include "psc_internal.h"
+
+namespace pscdev {
+
+// --------------------------------------------------------------------------------------------
+// K0: read range of every (sample, component).
+// The reference streams each BAM forward through the components in genome order; read x is
+// *examined* by the first component whose last subexon end is >= pos(x) on x's chromosome
+// (Constraints.cpp:272-283).  Both reads and components are sorted, so the reads examined by
+// component c are exactly those of its chromosome with pos in (maxEnd(c-1), maxEnd(c)].
+// --------------------------------------------------------------------------------------------
+PSC_DEV int upper_bound_pos(const int *pos, long long lo, long long hi, int key)
+{ // first index in [lo, hi) with pos > key
+	while (lo < hi) {
+		long long mid = (lo + hi) >> 1;
+		if (pos[mid] <= key) lo = mid + 1;
+		else hi = mid;
+	}
+	return (int)lo;
+}
+
+PSC_DEV void group_range_one(const GraphDev &g, const SampleDev &s, int c)
+{
+	int chr = g.comp_chr[c];
+	long long a = 0, b = 0;
+	if (chr >= 0 && chr < s.n_chr) {
+		a = s.chr_off[chr];
+		b = s.chr_off[chr + 1];
+	}
+	int lo = (int)a, hi = (int)a;
+	if (a < b) {
+		int pe = g.comp_prev_end[c];
+		lo = pe == INT32_MIN ? (int)a : upper_bound_pos(s.pos, a, b, pe);
+		hi = upper_bound_pos(s.pos, a, b, g.comp_max_end[c]);
+	}
+	s.grp_lo[c] = lo;
+	s.grp_hi[c] = hi;
+	int n = g.comp_off[c + 1] - g.comp_off[c];
+	// bits_off is turned into an exclusive prefix sum by the caller
+	s.bits_off[c] = (long long)(hi - lo) * ((n + 63) >> 6);
+}
+
+// --------------------------------------------------------------------------------------------
+// per-read conversion (Constraints.cpp:4-72 + 285-326).  Returns first (>=0) or -1.
+// --------------------------------------------------------------------------------------------
+PSC_DEV int convert_read(const GraphDev &g, const SampleDev &s, int c, int x, bool primaryAsUnique,
+                         uint64_t *bits, int W, int4 &meta)
+{
+	int base = g.comp_off[c], n = g.comp_off[c + 1] - base;
+	const int *sst = g.se_start + base, *sen = g.se_end + base, *pmx = g.se_pmax_end + base;
+	const int8_t *lt = g.lt + base, *rt = g.rt + base;
+	uint32_t so = s.seg_off[x];
+	int segCnt = (int)(s.seg_off[x + 1] - so);
+	const int *sa = s.seg_a + so, *sb = s.seg_b + so;
+	int pos = sa[0];
+	// tag: first subexon with end >= pos (Constraints.cpp:277)
+	int lo = 0, hi = n;
+	while (lo < hi) {
+		int mid = (lo + hi) >> 1;
+		if (pmx[mid] < pos) lo = mid + 1;
+		else hi = mid;
+	}
+	int tag = lo;
+	meta = make_int4(-1, -1, 0, 0);
+	if (tag >= n) return -1;
+	if (sb[segCnt - 1] < sst[tag]) return -1;
+	uint8_t fl = s.flags[x];
+	if (!(fl & 1)) return -1; // only primary alignments become constraints (Constraints.cpp:302)
+	for (int w = 0; w < W; ++w) bits[w] = 0;
+	int k = tag, first = -1, last = -1, cover = 0;
+	for (int i = 0; i < segCnt; ++i) {
+		int a = sa[i], b = sb[i];
+		cover += b - a + 1;
+		int leftIdx = -1, rightIdx = -1;
+		for (; k < n; ++k) {
+			int ss = sst[k], ee = sen[k];
+			if (ss > b) break;
+			if (a > ee) continue;
+			bool ok = (ss >= a && ee <= b) || (i == 0 && ss < a && ee <= b) ||
+			          (i == segCnt - 1 && ss >= a && ee > b) || (i == 0 && i == segCnt - 1 && ss < a && ee > b);
+			if (!ok) return -1;
+			if (leftIdx == -1) leftIdx = k;
+			rightIdx = k;
+			bt_set(bits, k);
+		}
+		if (leftIdx == -1) return -1;
+		if (!((lt[leftIdx] == 0 || sst[leftIdx] <= a) && (rt[rightIdx] == 0 || sen[rightIdx] >= b))) return -1;
+		if (i > 0) { // the intron must be an edge of the graph
+			int e0 = g.next_off[base + last], e1 = g.next_off[base + last + 1];
+			bool found = false;
+			for (int e = e0; e < e1; ++e)
+				if (g.next_idx[e] == leftIdx) { found = true; break; }
+			if (!found) return -1;
+		}
+		for (int j = leftIdx + 1; j <= rightIdx; ++j)
+			if (sst[j] > sen[j - 1] + 1) return -1;
+		if (i == 0) first = leftIdx;
+		last = rightIdx;
+	}
+	// clipped ends are only kept at true transcript ends (Constraints.cpp:310-326)
+	if (fl & 2) {
+		if ((first < n - 1 && sen[first] + 1 == sst[first + 1]) ||
+		    g.prev_off[base + first + 1] > g.prev_off[base + first] || (sb[0] - sa[0] + 1) <= cover / 3.0)
+			return -1;
+	}
+	if (fl & 4) {
+		int t = segCnt - 1;
+		if ((last > 0 && sst[last] - 1 == sen[last - 1]) || g.next_off[base + last + 1] > g.next_off[base + last] ||
+		    (sb[t] - sa[t] + 1) <= cover / 3.0)
+			return -1;
+	}
+	int uniq = primaryAsUnique ? 1 : ((fl & 16) ? 1 : 0);
+	int kind = 0; // 1 left mate, 2 right mate, 3 same-position first mate
+	if (fl & 32) {
+		int mp = s.mate_pos[x];
+		if (mp > pos) kind = 1;
+		else if (mp < pos) kind = 2;
+		else if (fl & 8) kind = 3;
+	}
+	meta = make_int4(first, last, cover, (int)s.nh[x] | (uniq << 8) | (kind << 16));
+	return first;
+}
+
+PSC_DEV uint64_t mix64(uint64_t z)
+{
+	z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+	z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+	return z ^ (z >> 31);
+}
+
+// --------------------------------------------------------------------------------------------
+// K1+K2 fused: one cooperative group builds the whole table of group (sample, comp).
+// --------------------------------------------------------------------------------------------
+PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, int c, bool primaryAsUnique)
+{
+	int lo = s.grp_lo[c], hi = s.grp_hi[c];
+	int R = hi - lo;
+	int base = g.comp_off[c], n = g.comp_off[c + 1] - base;
+	int W = (n + 63) >> 6;
+	if (R <= 0) {
+		if (co.lane == 0) { s.n_con[c] = 0; s.n_pair[c] = 0; }
+		return;
+	}
+	uint64_t *cbits = s.cand_bits + s.bits_off[c];
+	uint64_t *obits = s.con_bits + s.bits_off[c];
+	int *idx = s.sortbuf + 2 * (long long)lo;
+
+	// ---- A: convert every read; compact the accepted ones ----
+	int V = 0;
+	for (int b0 = 0; b0 < R; b0 += co.n) {
+		int r = b0 + co.lane;
+		bool ok = false;
+		if (r < R) {
+			int4 meta;
+			ok = convert_read(g, s, c, lo + r, primaryAsUnique, cbits + (long long)r * W, W, meta) >= 0;
+			s.cand_meta[lo + r] = meta;
+			s.cand_cid[lo + r] = -1;
+		}
+		uint32_t m = co.ballot(ok);
+		if (ok) idx[V + co.rank_in(m)] = r;
+		V += popc32(m);
+	}
+	co.sync();
+	if (V == 0) {
+		if (co.lane == 0) { s.n_con[c] = 0; s.n_pair[c] = 0; }
+		return;
+	}
+	// ---- B: sort by (first, bit-lexicographic) == CompSortConstraints ----
+	const int4 *meta = s.cand_meta + lo;
+	coop_sort(co, idx, V, [&](int a, int b) {
+		int fa = meta[a].x, fb = meta[b].x;
+		if (fa != fb) return fa < fb;
+		return cmp_bits_without_first(cbits + (long long)a * W, cbits + (long long)b * W, W) < 0;
+	});
+	// ---- C: run-length merge -> constraint rows ----
+	for (int r = co.lane; r < V; r += co.n) {
+		s.con_support[lo + r] = 0;
+		s.con_uniq[lo + r] = 0;
+		s.con_maxlen[lo + r] = 0;
+		s.con_nhcnt[lo + r] = make_int4(0, 0, 0, 0);
+	}
+	co.sync();
+	int C = 0;
+	for (int b0 = 0; b0 < V; b0 += co.n) {
+		int p = b0 + co.lane;
+		bool head = false;
+		int me = -1;
+		if (p < V) {
+			me = idx[p];
+			if (p == 0) head = true;
+			else {
+				int pv = idx[p - 1];
+				head = meta[me].x != meta[pv].x ||
+				       cmp_bits_without_first(cbits + (long long)me * W, cbits + (long long)pv * W, W) != 0;
+			}
+		}
+		uint32_t m = co.ballot(head);
+		if (p < V) {
+			int cid = C + popc32(m & ((2u << co.lane) - 1u)) - 1;
+			s.cand_cid[lo + me] = cid;
+			int4 mt = meta[me];
+			if (head) {
+				for (int w = 0; w < W; ++w) obits[(long long)cid * W + w] = cbits[(long long)me * W + w];
+				s.con_first[lo + cid] = mt.x;
+				s.con_last[lo + cid] = mt.y;
+			}
+			atomic_add(&s.con_support[lo + cid], 1);
+			atomic_add(&s.con_uniq[lo + cid], (mt.w >> 8) & 1);
+			atomic_max(&s.con_maxlen[lo + cid], mt.z);
+			int nh = mt.w & 0xff;
+			int *cnt = (int *)&s.con_nhcnt[lo + cid];
+			if (nh >= 1 && nh <= 4) atomic_add(&cnt[nh - 1], 1);
+		}
+		C += popc32(m);
+	}
+	co.sync();
+	// ---- D: mate pairs ----
+	int M = 0;
+	if (s.frag_stdev == 0) {
+		// single-end library: one (i, i) pair per constraint (Constraints.cpp:405-422)
+		for (int k = co.lane; k < C; k += co.n) {
+			s.pair_i[lo + k] = k;
+			s.pair_j[lo + k] = k;
+			s.pair_support[lo + k] = s.con_support[lo + k];
+			s.pair_uniq[lo + k] = s.con_uniq[lo + k];
+			s.pair_ec[lo + k] = 1;
+		}
+		M = C;
+	} else {
+		// join list: accepted reads that are a left or a right mate
+		int J = 0;
+		for (int b0 = 0; b0 < R; b0 += co.n) {
+			int r = b0 + co.lane;
+			int kind = 0;
+			if (r < R && meta[r].x >= 0) kind = (meta[r].w >> 16) & 3;
+			bool in = kind == 1 || kind == 2;
+			uint32_t m = co.ballot(in);
+			if (in) {
+				idx[J + co.rank_in(m)] = r;
+				// MateReadIds keys an entry by (read id, matePos); the right mate asks with its own pos
+				int jp = kind == 1 ? s.mate_pos[lo + r] : s.pos[lo + r];
+				s.pair_key[lo + r] = s.name_key[lo + r] ^ mix64((uint64_t)(uint32_t)jp + 0x9e3779b97f4a7c15ull);
+			}
+			J += popc32(m);
+		}
+		co.sync();
+		const uint64_t *jkey = s.pair_key + lo;
+		coop_sort(co, idx, J, [&](int a, int b) {
+			uint64_t ka = jkey[a], kb = jkey[b];
+			if (ka != kb) return ka < kb;
+			int ra = (meta[a].w >> 16) & 3, rb = (meta[b].w >> 16) & 3;
+			if (ra != rb) return ra < rb; // left mates (1) before right mates (2)
+			return a < b;
+		});
+		// every right mate looks back for the last left mate with its key (later insertions win)
+		// matches are recorded in cand_cid's sibling array pair_uniq_in as (left read) or -1
+		for (int p = co.lane; p < J; p += co.n) {
+			int me = idx[p];
+			int left = -1;
+			if (((meta[me].w >> 16) & 3) == 2) {
+				int q = p - 1;
+				while (q >= 0 && jkey[idx[q]] == jkey[me] && ((meta[idx[q]].w >> 16) & 3) == 2) --q;
+				if (q >= 0 && jkey[idx[q]] == jkey[me]) left = idx[q];
+			}
+			s.pair_uniq_in[lo + me] = left;
+		}
+		co.sync();
+		// pair list: (cid[left], cid[me]) for matched right mates, (cid, cid) for same-position first mates
+		int Pn = 0;
+		for (int b0 = 0; b0 < R; b0 += co.n) {
+			int r = b0 + co.lane;
+			bool in = false;
+			uint64_t key = 0;
+			if (r < R && meta[r].x >= 0) {
+				int kind = (meta[r].w >> 16) & 3;
+				int cj = s.cand_cid[lo + r];
+				if (kind == 2) {
+					int left = s.pair_uniq_in[lo + r];
+					if (left >= 0) {
+						in = true;
+						key = ((uint64_t)(uint32_t)s.cand_cid[lo + left] << 32) | (uint32_t)cj;
+					}
+				} else if (kind == 3) {
+					in = true;
+					key = ((uint64_t)(uint32_t)cj << 32) | (uint32_t)cj;
+				}
+			}
+			uint32_t m = co.ballot(in);
+			if (in) idx[Pn + co.rank_in(m)] = r;
+			Pn += popc32(m);
+			// keys are written after the left-read lookups of this chunk are done
+			co.sync();
+			if (in) s.pair_key[lo + r] = key;
+		}
+		co.sync();
+		const uint64_t *pkey = s.pair_key + lo;
+		coop_sort(co, idx, Pn, [&](int a, int b) {
+			uint64_t ka = pkey[a], kb = pkey[b];
+			if (ka != kb) return ka < kb;
+			return a < b;
+		});
+		for (int r = co.lane; r < Pn; r += co.n) {
+			s.pair_support[lo + r] = 0;
+			s.pair_uniq[lo + r] = 0;
+		}
+		co.sync();
+		for (int b0 = 0; b0 < Pn; b0 += co.n) {
+			int p = b0 + co.lane;
+			bool head = false;
+			int me = -1;
+			if (p < Pn) {
+				me = idx[p];
+				head = p == 0 || pkey[me] != pkey[idx[p - 1]];
+			}
+			uint32_t m = co.ballot(head);
+			if (p < Pn) {
+				int pid = M + popc32(m & ((2u << co.lane) - 1u)) - 1;
+				if (head) {
+					s.pair_i[lo + pid] = (int)(pkey[me] >> 32);
+					s.pair_j[lo + pid] = (int)(pkey[me] & 0xffffffffu);
+					s.pair_ec[lo + pid] = 2;
+				}
+				atomic_add(&s.pair_support[lo + pid], 1);
+				atomic_add(&s.pair_uniq[lo + pid], (meta[me].w >> 8) & 1);
+			}
+			M += popc32(m);
+		}
+	}
+	co.sync();
+	// ---- E: weights, effective lengths, normalised abundance (Constraints.cpp:152-238) ----
+	const int *sst = g.se_start + base, *sen = g.se_end + base;
+	const int8_t *lt = g.lt + base, *rt = g.rt + base;
+	for (int k = co.lane; k < C; k += co.n) {
+		int4 nhc = s.con_nhcnt[lo + k];
+		// sum of (1.0/NH)*10 over the merged reads; exact (order-free) for NH in {1,2,4}
+		double weight = ((nhc.x * 10.0 + nhc.y * 5.0) + nhc.w * 2.5) + nhc.z * ((1.0 / 3) * 10);
+		int first = s.con_first[lo + k], last = s.con_last[lo + k];
+		const uint64_t *b = obits + (long long)k * W;
+		int readLen = s.con_maxlen[lo + k];
+		if (first + 1 < last)
+			for (int q = first + 1; q < last; ++q)
+				if (bt_test(b, q)) readLen -= sen[q] - sst[q] + 1;
+		int eff;
+		if (first == last) {
+			eff = (sen[first] - readLen + 1) - sst[first] + 1;
+			if (eff <= 0) eff = (sen[first] - sst[first] + 1) / 2 + 1;
+		} else {
+			int start = sen[first] + 1 - (readLen - 1), end;
+			if (start < sst[first]) start = sst[first];
+			if (sen[last] - sst[last] + 1 >= readLen - 1 || rt[last] == 0) end = sen[first];
+			else end = sen[first] + 1 - (readLen - (sen[last] - sst[last] + 1));
+			if (end < start) end = sst[first];
+			eff = end - start + 1;
+		}
+		double na = weight / (double)eff;
+		if ((lt[first] == 0 && sen[first] - sst[first] + 1 >= 8 * s.read_len) ||
+		    (rt[last] == 0 && sen[last] - sst[last] + 1 >= 8 * s.read_len))
+			na *= 2;
+		s.con_weight[lo + k] = weight;
+		s.con_norm[lo + k] = na;
+	}
+	co.sync();
+	for (int k = co.lane; k < M; k += co.n) {
+		int i = s.pair_i[lo + k], j = s.pair_j[lo + k];
+		double a = s.con_norm[lo + i], b = s.con_norm[lo + j];
+		double v = a < b ? a : b;
+		if (i != j) {
+			if (lt[s.con_first[lo + i]] == 0 && s.con_first[lo + i] == s.con_last[lo + i] && a < b) v = b;
+			else if (rt[s.con_last[lo + j]] == 0 && s.con_first[lo + j] == s.con_last[lo + j] && a > b) v = a;
+		}
+		s.pair_norm[lo + k] = v;
+	}
+	if (co.lane == 0) {
+		s.n_con[c] = C;
+		s.n_pair[c] = M;
+	}
+}
+
+} // namespace pscdev

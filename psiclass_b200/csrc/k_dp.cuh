@@ -1,0 +1,976 @@
+// k_dp.cuh -- candidate generation by dynamic programming for complex components:
+// PickTranscriptsByDP / SolveSubTranscript / SearchSubTranscript / AugmentTranscripts /
+// CoalesceSameTranscripts (TranscriptDecider.cpp:303-328, 374-1365) and the per-sample driver
+// loop of Solve (TranscriptDecider.cpp:3139-3265).
+//
+// The two mutually recursive functions of the reference become one explicit-stack machine whose
+// control state is uniform across the cooperative group; the scans over the constraint list
+// (cover counting, extension collection) are strided across the lanes.  The depth-first order and
+// the strict '>' updates of the reference are preserved, so the chosen paths are identical.
+#pragma once
+
+namespace pscdev {
+
+struct DpMemo {
+	double cover, minAbundance;
+	int first, last, cnt, timeStamp, strand, epoch;
+};
+
+struct DpScratch {
+	// memo: f1 [n], f2 [n*n], hash [hashMax]; an entry is valid only when epoch matches
+	DpMemo *ent;
+	uint64_t *ebits;
+	long long f2Base, hashBase;
+	int hashMax;
+	// constraints handed to the DP for the current sample (possibly truncated / down-sampled)
+	uint64_t *tcb;
+	int *tcf, *tcl, *tcsup;
+	double *tcnorm, *tcab;
+	int tcCnt;
+	uint8_t *uncov; // per next-edge of the component
+	int *P;         // the path stack: solve keys and search extensions share it
+	int *fr;        // frames
+	double *fdcover;
+	int *fdmeta; // first,last,strand per solve frame
+	uint64_t *fdbits;
+	int *ext;
+	int extCap;
+	double *ckey;
+	DpMemo *cent;
+	uint64_t *cbits;
+	uint8_t *cvalid;
+	int cCap;
+	uint64_t *txb;
+	int *txf, *txl;
+	int txCap;
+	uint64_t *work; // [8*W]
+	int *covered;
+	int *sortidx;
+	// second candidate buffer for the permutation step of CoalesceSameTranscripts
+	uint64_t *c2b;
+	int *c2f, *c2l;
+};
+
+#define PSC_FR_INTS 10
+__host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, int n, int E, int Cmax, long long candCap)
+{
+	Carver cv(base);
+	int W = (n + 63) >> 6;
+	DpScratch s;
+	s.hashMax = n > 500 ? 1000003 : 100003; // Q3: the other branches of the reference are unreachable
+	long long nEnt = (long long)n + (long long)n * n + s.hashMax;
+	s.f2Base = n;
+	s.hashBase = (long long)n + (long long)n * n;
+	s.ent = cv.take<DpMemo>((size_t)nEnt);
+	s.ebits = cv.take<uint64_t>((size_t)nEnt * W);
+	s.tcb = cv.take<uint64_t>((size_t)Cmax * W + 1);
+	s.tcf = cv.take<int>((size_t)Cmax + 1);
+	s.tcl = cv.take<int>((size_t)Cmax + 1);
+	s.tcsup = cv.take<int>((size_t)Cmax + 1);
+	s.tcnorm = cv.take<double>((size_t)Cmax + 1);
+	s.tcab = cv.take<double>((size_t)Cmax + 1);
+	s.tcCnt = 0;
+	s.uncov = cv.take<uint8_t>((size_t)E + 1);
+	s.P = cv.take<int>((size_t)n + 4);
+	s.fr = cv.take<int>((size_t)(2 * n + 6) * PSC_FR_INTS);
+	s.fdcover = cv.take<double>((size_t)n + 3);
+	s.fdmeta = cv.take<int>((size_t)(n + 3) * 3);
+	s.fdbits = cv.take<uint64_t>((size_t)(n + 3) * W);
+	long long ec = (long long)(n + 2) * (Cmax + 1);
+	if (ec > (long long)4 << 20) ec = (long long)4 << 20;
+	s.extCap = (int)ec;
+	s.ext = cv.take<int>((size_t)s.extCap);
+	s.cCap = Cmax + 2;
+	s.ckey = cv.take<double>((size_t)s.cCap);
+	s.cent = cv.take<DpMemo>((size_t)s.cCap);
+	s.cbits = cv.take<uint64_t>((size_t)s.cCap * W);
+	s.cvalid = cv.take<uint8_t>((size_t)s.cCap);
+	s.txCap = Cmax + 2;
+	s.txb = cv.take<uint64_t>((size_t)s.txCap * W);
+	s.txf = cv.take<int>((size_t)s.txCap);
+	s.txl = cv.take<int>((size_t)s.txCap);
+	s.work = cv.take<uint64_t>((size_t)8 * W);
+	s.covered = cv.take<int>((size_t)Cmax + 1);
+	long long p2 = 1;
+	while (p2 < candCap + 1) p2 <<= 1;
+	s.sortidx = cv.take<int>((size_t)p2 + 1);
+	s.c2b = cv.take<uint64_t>((size_t)candCap * W + 1);
+	s.c2f = cv.take<int>((size_t)candCap + 1);
+	s.c2l = cv.take<int>((size_t)candCap + 1);
+	if (o) *o = s;
+	return (cv.off + 15) & ~(size_t)15;
+}
+// bytes at the start of the scratch that must be zero before the first use (memo epochs)
+__host__ __device__ inline size_t dp_scratch_zero_bytes(int n)
+{
+	int hashMax = n > 500 ? 1000003 : 100003;
+	long long nEnt = (long long)n + (long long)n * n + hashMax;
+	return (size_t)nEnt * sizeof(DpMemo);
+}
+
+struct DpState {
+	Coop co;
+	CompView v;
+	DpScratch d;
+	const uint8_t *cs, *ce;
+	int W;
+	bool forAbundance;
+	double minAbundance;
+	int timeStamp, epoch;
+	int *err;
+};
+
+PSC_DEV bool dp_edge_uncovered(const DpState &st, int a, int b)
+{
+	for (int e = st.v.noff[a]; e < st.v.noff[a + 1]; ++e)
+		if (st.v.nidx[e] == b) return st.d.uncov[e - st.v.noff[0]] != 0;
+	return false;
+}
+
+// first index >= from whose constraint starts after `bound` (constraints are sorted by .first)
+PSC_DEV int dp_tc_end(const DpState &st, int from, int bound)
+{
+	int lo = from, hi = st.d.tcCnt;
+	while (lo < hi) {
+		int mid = (lo + hi) >> 1;
+		if (st.d.tcf[mid] <= bound) lo = mid + 1;
+		else hi = mid;
+	}
+	return lo;
+}
+
+// the three cover scans of the reference (.cpp:463-490, 569-596, 732-755), lane-parallel.
+// All reductions are order-free: a count of integers, a minimum, or "any".
+PSC_DEV double dp_scan_cover(const DpState &st, const uint64_t *tb, int tf, int tl, int tcStart, int bound, double cover,
+                             bool &belowMin)
+{
+	int end = dp_tc_end(st, tcStart, bound);
+	int below = 0, cnt = 0;
+	double mn = 1e300;
+	for (int i = tcStart + st.co.lane; i < end; i += st.co.n) {
+		if (compat(tb, tf, tl, false, st.d.tcb + (long long)i * st.W, st.d.tcf[i], st.d.tcl[i], st.W) != 1) continue;
+		if (st.d.tcnorm[i] <= st.minAbundance) { below = 1; continue; }
+		if (st.d.tcab[i] <= 0) continue;
+		++cnt;
+		if (st.d.tcnorm[i] < mn) mn = st.d.tcnorm[i];
+	}
+	// a below-minimum constraint only counts if no earlier one... no: the reference breaks at the FIRST
+	// compatible constraint with normAbund <= minAbundance, whatever was counted before, and returns -2
+	below = st.co.max(below);
+	if (below) {
+		belowMin = true;
+		return -2;
+	}
+	if (st.forAbundance) {
+		mn = st.co.min(mn);
+		cnt = st.co.sum(cnt);
+		if (cnt > 0) {
+			if (cover == 0 || mn < cover) cover = mn;
+		}
+		return cover;
+	}
+	cnt = st.co.sum(cnt);
+	return cover + cnt;
+}
+
+PSC_DEV void dp_bits_from_path(const DpState &st, uint64_t *dst, const int *p, int cnt, bool clear)
+{
+	// uniform scalar code executed by lane 0 only; callers sync
+	if (st.co.lane != 0) return;
+	if (clear)
+		for (int w = 0; w < st.W; ++w) dst[w] = 0;
+	for (int i = 0; i < cnt; ++i) bt_set(dst, p[i]);
+}
+
+PSC_DEV long long dp_memo_index(const DpState &st, const int *visit, int vcnt)
+{
+	if (vcnt == 1) return visit[0];
+	if (vcnt == 2) return st.d.f2Base + (long long)visit[0] * st.v.n + visit[1]; // seCnt <= 10000 is enforced by the host
+	long long key = 0;
+	for (int i = 0; i < vcnt; ++i) key = (key * st.v.n + visit[i]) % st.d.hashMax;
+	return st.d.hashBase + key;
+}
+
+// frame layout (ints): 0 type, 1 state, 2 a, 3 b, 4 c, 5 d, 6 e, 7 f, 8 g, 9 h
+//  solve : a=vbase b=vcnt c=strand d=tcStart e=extBase f=extCnt g=edge iterator h=dp slot
+//  search: a=tag  b=strand c=owner frame d=vcnt(after) e=extCnt f=edge iterator g=keepSearch
+#define FR(i, k) st.d.fr[(i) * PSC_FR_INTS + (k)]
+
+// One call of SolveSubTranscript(visit = {start}, strand 0) with everything below it.  The result
+// (cover + path) is left in the memo entry whose index is returned.
+PSC_DEVN long long dp_solve_root(DpState &st, int start)
+{
+	const Coop &co = st.co;
+	const CompView &v = st.v;
+	DpScratch &d = st.d;
+	int W = st.W;
+	int sp = 0, extTop = 0, dpTop = 0;
+	long long ret = -1;
+	uint64_t *sub = d.work + 2 * W; // the reference's attr.bufferTxpt
+	// push root
+	co.sync();
+	if (co.lane == 0) {
+		d.P[0] = start;
+		FR(0, 0) = 0; FR(0, 1) = 0; FR(0, 2) = 0; FR(0, 3) = 1; FR(0, 4) = 0; FR(0, 5) = 0;
+	}
+	sp = 1;
+	co.sync();
+	while (sp > 0) {
+		int fi = sp - 1;
+		int type = FR(fi, 0), state = FR(fi, 1);
+		if (type == 0) {
+			// ================= SolveSubTranscript =================
+			int vbase = FR(fi, 2), vcnt = FR(fi, 3), strand = FR(fi, 4);
+			const int *visit = d.P + vbase;
+			long long mi = dp_memo_index(st, visit, vcnt);
+			DpMemo *me = d.ent + mi;
+			uint64_t *mbits = d.ebits + mi * W;
+			if (state == 0) {
+				// ---- memo probe (.cpp:652-706) ----
+				bool hit = false;
+				if (me->epoch == st.epoch && me->cover != -1 && me->strand == strand &&
+				    (me->timeStamp == st.timeStamp || (me->minAbundance < st.minAbundance && me->cover == -2))) {
+					if (vcnt <= 2) hit = true;
+					else if (me->cnt == vcnt && me->first == visit[0]) {
+						// the first vcnt subexons of the stored path must be this key
+						bool same = true;
+						int lo = visit[0], hi = visit[vcnt - 1];
+						int k = 0;
+						for (int q = lo; q <= hi && same; ++q) {
+							bool inKey = k < vcnt && visit[k] == q;
+							if (inKey) ++k;
+							if (bt_test(mbits, q) != inKey) same = false;
+						}
+						hit = same;
+					}
+				}
+				if (hit) {
+					ret = mi;
+					--sp;
+					continue;
+				}
+				// ---- fresh evaluation ----
+				int tcStart = FR(fi, 5);
+				{
+					int lo = tcStart, hi = d.tcCnt;
+					while (lo < hi) { // first constraint with first >= visit[0]
+						int mid = (lo + hi) >> 1;
+						if (d.tcf[mid] < visit[0]) lo = mid + 1;
+						else hi = mid;
+					}
+					tcStart = lo;
+				}
+				int slot = dpTop++;
+				uint64_t *vb = d.fdbits + (long long)slot * W;
+				int last = visit[vcnt - 1];
+				co.sync();
+				dp_bits_from_path(st, sub, visit, vcnt, true);
+				co.sync();
+				double cover = -1;
+				if (st.ce[last]) {
+					bool bm = false;
+					cover = dp_scan_cover(st, sub, visit[0], last, tcStart, last, 0, bm);
+				}
+				// extensions: constraints whose head matches the tail of the partial path
+				int extBase = extTop, extCnt = 0;
+				{
+					int end = dp_tc_end(st, tcStart, last);
+					for (int b0 = tcStart; b0 < end; b0 += co.n) {
+						int i = b0 + co.lane;
+						bool is = i < end && compat(sub, visit[0], last, true, d.tcb + (long long)i * W, d.tcf[i], d.tcl[i], W) == 2;
+						uint32_t m = co.ballot(is);
+						if (is) {
+							int p = extBase + extCnt + co.rank_in(m);
+							if (p < d.extCap) d.ext[p] = i;
+						}
+						extCnt += popc32(m);
+					}
+					if (extBase + extCnt > d.extCap) {
+						*st.err = 21;
+						extCnt = d.extCap - extBase;
+					}
+					co.sync();
+					// stable sort by .last (.cpp:781-796; glibc qsort == merge sort): insertion sort, lists are short
+					if (co.lane == 0)
+						for (int a = 1; a < extCnt; ++a) {
+							int x = d.ext[extBase + a], xl = d.tcl[x], b = a - 1;
+							while (b >= 0 && d.tcl[d.ext[extBase + b]] > xl) { d.ext[extBase + b + 1] = d.ext[extBase + b]; --b; }
+							d.ext[extBase + b + 1] = x;
+						}
+				}
+				extTop = extBase + extCnt;
+				if (co.lane == 0) {
+					for (int w = 0; w < W; ++w) vb[w] = sub[w];
+					d.fdcover[slot] = cover;
+					d.fdmeta[slot * 3 + 0] = visit[0];
+					d.fdmeta[slot * 3 + 1] = last;
+					d.fdmeta[slot * 3 + 2] = strand;
+					FR(fi, 1) = 1;
+					FR(fi, 5) = tcStart;
+					FR(fi, 6) = extBase;
+					FR(fi, 7) = extCnt;
+					FR(fi, 8) = v.noff[last];
+					FR(fi, 9) = slot;
+				}
+				co.sync();
+				continue;
+			}
+			// ---- state 1: iterate the successors of the last subexon of the key (.cpp:798-819) ----
+			{
+				int a = visit[vcnt - 1];
+				int ei = FR(fi, 8);
+				bool pushed = false;
+				while (ei < v.noff[a + 1]) {
+					int b = v.nidx[ei++];
+					if ((same_strand(v.rs[a], strand) && same_strand(v.ls[b], strand)) || v.st[b] == v.en[a] + 1) {
+						int ns = strand;
+						if (v.st[b] > v.en[a] + 1) ns = v.rs[a];
+						co.sync();
+						if (co.lane == 0) {
+							FR(fi, 8) = ei;
+							FR(sp, 0) = 1; FR(sp, 1) = 0; FR(sp, 2) = b; FR(sp, 3) = ns; FR(sp, 4) = fi; FR(sp, 5) = 0;
+							FR(sp, 6) = FR(fi, 7);
+						}
+						++sp;
+						co.sync();
+						pushed = true;
+						break;
+					}
+				}
+				if (pushed) continue;
+				// ---- done: store in the memo (.cpp:824-856) ----
+				int slot = FR(fi, 9);
+				co.sync();
+				if (co.lane == 0) {
+					const uint64_t *vb = d.fdbits + (long long)slot * W;
+					for (int w = 0; w < W; ++w) mbits[w] = vb[w];
+					me->first = d.fdmeta[slot * 3 + 0];
+					me->last = d.fdmeta[slot * 3 + 1];
+					me->strand = d.fdmeta[slot * 3 + 2];
+					me->cover = d.fdcover[slot];
+					me->cnt = vcnt;
+					me->minAbundance = st.minAbundance;
+					me->timeStamp = st.timeStamp;
+					me->epoch = st.epoch;
+				}
+				co.sync();
+				extTop = FR(fi, 6);
+				dpTop = slot;
+				ret = mi;
+				--sp;
+				continue;
+			}
+		}
+		// ================= SearchSubTranscript =================
+		int tag = FR(fi, 2), strand = FR(fi, 3), owner = FR(fi, 4);
+		int ovbase = FR(owner, 2), pcnt = FR(owner, 3), tcStart = FR(owner, 5), oslot = FR(owner, 9);
+		const int *parents = d.P + ovbase;
+		int *visit = d.P + ovbase + pcnt;
+		uint64_t *pb = d.fdbits + (long long)oslot * W; // pdp.seVector
+		if (state == 0) {
+			int vcnt = FR(fi, 5) + 1;
+			int extCnt = FR(fi, 6);
+			co.sync();
+			if (co.lane == 0) {
+				visit[vcnt - 1] = tag;
+				for (int w = 0; w < W; ++w) sub[w] = 0;
+				for (int i = 0; i < pcnt; ++i) bt_set(sub, parents[i]);
+				for (int i = 0; i < vcnt; ++i) bt_set(sub, visit[i]);
+			}
+			co.sync();
+			// drop the pending extensions that no longer fit (.cpp:407-412)
+			{
+				const int *ext = d.ext + FR(owner, 6);
+				int i;
+				for (i = extCnt - 1; i >= 0; --i) {
+					int x = ext[i];
+					if (d.tcl[x] <= tag ||
+					    (bt_test(d.tcb + (long long)x * W, tag) &&
+					     compat(sub, parents[0], tag, true, d.tcb + (long long)x * W, d.tcf[x], d.tcl[x], W) != 0))
+						break;
+				}
+				extCnt = i + 1;
+			}
+			bool solveHere = v.noff[tag + 1] > v.noff[tag] &&
+			                 (extCnt == 0 || tag >= d.tcl[d.ext[FR(owner, 6) + extCnt - 1]]);
+			co.sync();
+			if (co.lane == 0) {
+				FR(fi, 5) = vcnt;
+				FR(fi, 6) = extCnt;
+				FR(fi, 8) = solveHere ? 0 : 1; // keepSearch
+				FR(fi, 1) = 1;
+			}
+			if (solveHere) {
+				// the sub-problem is keyed by the walk since the owner's key: it already sits in P
+				if (co.lane == 0) {
+					FR(sp, 0) = 0; FR(sp, 1) = 0; FR(sp, 2) = ovbase + pcnt; FR(sp, 3) = vcnt; FR(sp, 4) = strand;
+					FR(sp, 5) = tcStart;
+				}
+				++sp;
+				ret = -1;
+				co.sync();
+				continue;
+			}
+			ret = -1;
+			co.sync();
+			state = 1; // fall through with no sub-solution
+		}
+		if (state == 1) {
+			int vcnt = FR(fi, 5);
+			bool keepSearch = FR(fi, 8) != 0;
+			double vcover = -1;
+			const uint64_t *vbits = nullptr;
+			int vlast = -1;
+			if (!keepSearch && ret >= 0) {
+				vcover = d.ent[ret].cover;
+				vbits = d.ebits + ret * W;
+				vlast = d.ent[ret].last;
+			}
+			double pcover = d.fdcover[oslot];
+			bool belowMin = false;
+			if (vcover >= 0) {
+				double cover = vcover;
+				co.sync();
+				if (co.lane == 0) {
+					for (int w = 0; w < W; ++w) sub[w] = vbits[w];
+					for (int i = 0; i < pcnt; ++i) bt_set(sub, parents[i]);
+				}
+				co.sync();
+				if (!st.forAbundance && st.minAbundance > 0) {
+					for (int i = 0; i < pcnt - 1; ++i)
+						if (dp_edge_uncovered(st, parents[i], parents[i + 1])) belowMin = true;
+					for (int i = -1; i < vcnt - 1; ++i) {
+						if (i == -1 && pcnt >= 1) {
+							if (dp_edge_uncovered(st, parents[pcnt - 1], visit[0])) belowMin = true;
+						} else if (dp_edge_uncovered(st, visit[i], visit[i + 1]))
+							belowMin = true;
+					}
+				}
+				bool bm2 = false;
+				cover = dp_scan_cover(st, sub, parents[0], vlast, tcStart, parents[pcnt - 1], cover, bm2);
+				if (bm2) belowMin = true;
+				bool takeBelow = belowMin && pcover == -1;
+				if (takeBelow || (!(belowMin && pcover == -1) && cover > pcover)) {
+					co.sync();
+					if (co.lane == 0) {
+						d.fdcover[oslot] = takeBelow ? -2 : cover;
+						for (int w = 0; w < W; ++w) pb[w] = sub[w];
+						d.fdmeta[oslot * 3 + 0] = parents[0];
+						d.fdmeta[oslot * 3 + 1] = vlast;
+						d.fdmeta[oslot * 3 + 2] = strand;
+					}
+					co.sync();
+					pcover = takeBelow ? -2 : cover;
+				}
+			} else if (vcover == -2 && pcover == -1) {
+				co.sync();
+				if (co.lane == 0) {
+					for (int w = 0; w < W; ++w) pb[w] = vbits[w];
+					for (int i = 0; i < pcnt; ++i) bt_set(pb, parents[i]);
+					d.fdcover[oslot] = -2;
+					d.fdmeta[oslot * 3 + 0] = parents[0];
+					d.fdmeta[oslot * 3 + 1] = vlast;
+					d.fdmeta[oslot * 3 + 2] = strand;
+				}
+				co.sync();
+				pcover = -2;
+			}
+			// the path may also stop at this subexon (.cpp:524-614)
+			if (st.ce[tag] && (vcover < 0 || st.forAbundance)) {
+				bool below = false;
+				co.sync();
+				if (co.lane == 0) {
+					for (int w = 0; w < W; ++w) sub[w] = 0;
+					for (int i = 0; i < pcnt; ++i) bt_set(sub, parents[i]);
+					for (int i = 0; i < vcnt; ++i) bt_set(sub, visit[i]);
+				}
+				co.sync();
+				double cover = 0;
+				if (st.forAbundance || st.minAbundance > 0) {
+					for (int i = 0; i < pcnt - 1; ++i)
+						if (dp_edge_uncovered(st, parents[i], parents[i + 1])) below = true;
+					for (int i = -1; i < vcnt - 1; ++i) {
+						if (i == -1 && pcnt >= 1) {
+							if (dp_edge_uncovered(st, parents[pcnt - 1], visit[0])) below = true;
+						} else if (dp_edge_uncovered(st, visit[i], visit[i + 1]))
+							below = true;
+					}
+					if (st.forAbundance && below) cover = 1e-6;
+				}
+				bool bm2 = false;
+				cover = dp_scan_cover(st, sub, parents[0], visit[vcnt - 1], tcStart, visit[vcnt - 1], cover, bm2);
+				if (bm2) below = true;
+				bool takeBelow = below && pcover == -1;
+				if (takeBelow || (!(below && pcover == -1) && cover > pcover)) {
+					co.sync();
+					if (co.lane == 0) {
+						d.fdcover[oslot] = takeBelow ? -2 : cover;
+						for (int w = 0; w < W; ++w) pb[w] = sub[w];
+						d.fdmeta[oslot * 3 + 0] = parents[0];
+						d.fdmeta[oslot * 3 + 1] = visit[vcnt - 1];
+						d.fdmeta[oslot * 3 + 2] = strand;
+					}
+					co.sync();
+				}
+			}
+			if (!keepSearch) {
+				--sp;
+				ret = -1;
+				continue;
+			}
+			co.sync();
+			if (co.lane == 0) {
+				FR(fi, 1) = 2;
+				FR(fi, 7) = v.noff[tag];
+			}
+			co.sync();
+			state = 2;
+		}
+		// ---- state 2: keep walking (.cpp:618-637) ----
+		{
+			int vcnt = FR(fi, 5);
+			int ei = FR(fi, 7);
+			bool pushed = false;
+			while (ei < v.noff[tag + 1]) {
+				int b = v.nidx[ei++];
+				if ((same_strand(v.rs[tag], strand) && same_strand(v.ls[b], strand)) || v.st[b] == v.en[tag] + 1) {
+					int ns = strand;
+					if (v.st[b] > v.en[tag] + 1) ns = v.rs[tag];
+					co.sync();
+					if (co.lane == 0) {
+						FR(fi, 7) = ei;
+						FR(sp, 0) = 1; FR(sp, 1) = 0; FR(sp, 2) = b; FR(sp, 3) = ns; FR(sp, 4) = owner; FR(sp, 5) = vcnt;
+						FR(sp, 6) = FR(fi, 6);
+					}
+					++sp;
+					co.sync();
+					pushed = true;
+					break;
+				}
+			}
+			if (pushed) continue;
+			--sp;
+			ret = -1;
+		}
+	}
+	co.sync();
+	return ret;
+}
+#undef FR
+
+// copy a memo entry into one of the two "best so far" registers kept in work[] (SetDpContent)
+struct DpBest {
+	double cover;
+	int first, last;
+	uint64_t *bits;
+};
+PSC_DEV void dp_take(const DpState &st, DpBest &dst, const uint64_t *bits, double cover, int first, int last)
+{
+	st.co.sync();
+	if (st.co.lane == 0)
+		for (int w = 0; w < st.W; ++w) dst.bits[w] = bits[w];
+	dst.cover = cover;
+	dst.first = first;
+	dst.last = last;
+	st.co.sync();
+}
+
+// PickTranscriptsByDP (TranscriptDecider.cpp:860-1201) on the constraints currently loaded in
+// st.d.tc*; the new transcripts are appended to st.d.tx* and their count returned.
+PSC_DEVN int dp_pick(DpState &st, int iterBound)
+{
+	const Coop &co = st.co;
+	const CompView &v = st.v;
+	DpScratch &d = st.d;
+	int W = st.W, n = v.n, tcCnt = d.tcCnt;
+	st.timeStamp = 1;
+	++st.epoch;
+	// ---- uncovered edges (.cpp:890-947): lanes over edges ----
+	{
+		int e0 = v.noff[0];
+		for (int i = 0; i < n; ++i)
+			for (int e = v.noff[i] + co.lane; e < v.noff[i + 1]; e += co.n) {
+				int nb = v.nidx[e];
+				bool covered = false;
+				int end = dp_tc_end(st, 0, i);
+				for (int l = 0; l < end && !covered; ++l) {
+					if (d.tcl[l] < i) continue;
+					const uint64_t *b = d.tcb + (long long)l * W;
+					if (!(bt_test(b, i) && bt_test(b, nb))) continue;
+					bool between = false;
+					for (int q = i + 1; q < nb; ++q)
+						if (bt_test(b, q)) { between = true; break; }
+					if (!between) covered = true;
+				}
+				d.uncov[e - e0] = covered ? 0 : 1;
+			}
+		co.sync();
+	}
+	// ---- abundance of the most abundant path (.cpp:951-966) ----
+	double maxAbundance = -1;
+	st.forAbundance = true;
+	st.minAbundance = 0;
+	for (int i = 0; i < n; ++i)
+		if (st.cs[i]) {
+			long long r = dp_solve_root(st, i);
+			double c = d.ent[r].cover;
+			if (c > maxAbundance) maxAbundance = c;
+		}
+	st.forAbundance = false;
+	for (int k = co.lane; k < d.cCap; k += co.n) d.cvalid[k] = 0;
+	co.sync();
+	DpBest maxCover, best;
+	maxCover.bits = d.work;
+	best.bits = d.work + W;
+	uint64_t *sub = d.work + 2 * W;
+	int iterCnt = 0, txCnt = 0;
+	for (;;) {
+		double bestScore = -1;
+		st.minAbundance = 0;
+		best.cover = -1;
+		for (;;) {
+			// cached result for this minAbundance? (.cpp:996-1000)
+			int hit = -1;
+			for (int k = 0; k < d.cCap; ++k)
+				if (d.cvalid[k] && d.ckey[k] == st.minAbundance) { hit = k; break; }
+			if (hit >= 0) {
+				dp_take(st, maxCover, d.cbits + (long long)hit * W, d.cent[hit].cover, d.cent[hit].first, d.cent[hit].last);
+			} else {
+				maxCover.cover = -1;
+				++st.timeStamp;
+				for (int i = 0; i < n; ++i) {
+					if (!st.cs[i]) continue;
+					long long r = dp_solve_root(st, i);
+					double c = d.ent[r].cover;
+					if (c > maxCover.cover && c > 0) dp_take(st, maxCover, d.ebits + r * W, c, d.ent[r].first, d.ent[r].last);
+				}
+				if (maxCover.cover == -1) break;
+				int slot = -1;
+				for (int k = 0; k < d.cCap; ++k)
+					if (!d.cvalid[k]) { slot = k; break; }
+				if (slot < 0) {
+					*st.err = 22;
+					slot = 0;
+				}
+				co.sync();
+				if (co.lane == 0) {
+					d.cvalid[slot] = 1;
+					d.ckey[slot] = st.minAbundance;
+					d.cent[slot].cover = maxCover.cover;
+					d.cent[slot].first = maxCover.first;
+					d.cent[slot].last = maxCover.last;
+					for (int w = 0; w < W; ++w) d.cbits[(long long)slot * W + w] = maxCover.bits[w];
+				}
+				co.sync();
+			}
+			// bottleneck abundance of the max-cover path (.cpp:1028-1055)
+			double mn = 1e300;
+			int anyc = 0;
+			for (int i = co.lane; i < tcCnt; i += co.n)
+				if (compat(maxCover.bits, maxCover.first, maxCover.last, false, d.tcb + (long long)i * W, d.tcf[i], d.tcl[i], W) == 1) {
+					anyc = 1;
+					if (d.tcnorm[i] < mn) mn = d.tcnorm[i];
+				}
+			mn = co.min(mn);
+			anyc = co.max(anyc);
+			double min = anyc ? mn : -1;
+			if (st.minAbundance == 0) {
+				int prev = -1;
+				for (int q = maxCover.first; q <= maxCover.last; ++q) {
+					if (!bt_test(maxCover.bits, q)) continue;
+					if (prev >= 0 && dp_edge_uncovered(st, prev, q)) { min = 1e-6; break; }
+					prev = q;
+				}
+			}
+			double score = compute_score(maxCover.cover, 1.0, min, maxAbundance, 0);
+			if (bestScore == -1 || score > bestScore) {
+				bestScore = score;
+				dp_take(st, best, maxCover.bits, maxCover.cover, maxCover.first, maxCover.last);
+			} else if (score < bestScore) {
+				if (compute_score(maxCover.cover, 1.0, maxAbundance, maxAbundance, 0) < bestScore) break;
+			}
+			st.minAbundance = min;
+		}
+		if (best.cover == -1) break;
+		// ---- assign the constraints of the best path (.cpp:1074-1152) ----
+		int coveredCnt = 0;
+		double update = 1e300;
+		int anyu = 0;
+		for (int b0 = 0; b0 < tcCnt; b0 += co.n) {
+			int i = b0 + co.lane;
+			bool is = i < tcCnt && compat(best.bits, best.first, best.last, false, d.tcb + (long long)i * W, d.tcf[i], d.tcl[i], W) == 1;
+			uint32_t m = co.ballot(is);
+			if (is) {
+				d.covered[coveredCnt + co.rank_in(m)] = i;
+				if (d.tcab[i] > 0) { anyu = 1; if (d.tcab[i] < update) update = d.tcab[i]; }
+			}
+			coveredCnt += popc32(m);
+		}
+		update = co.min(update);
+		anyu = co.max(anyu);
+		if (!anyu) update = -1;
+		update *= (1 + iterCnt / 50); // Q7: integer division
+		co.sync();
+		if (txCnt < d.txCap) {
+			if (co.lane == 0) {
+				for (int w = 0; w < W; ++w) d.txb[(long long)txCnt * W + w] = best.bits[w];
+				d.txf[txCnt] = best.first;
+				d.txl[txCnt] = best.last;
+			}
+			++txCnt;
+		} else
+			*st.err = 23;
+		// subtract; a constraint that runs dry invalidates the cached paths containing it
+		for (int q = 0; q < coveredCnt; ++q) {
+			int j = d.covered[q];
+			double ab = d.tcab[j];
+			if (ab > 0) {
+				double tmp = ab > update ? update : ab;
+				ab -= tmp;
+				if (ab <= 0) {
+					for (int k = co.lane; k < d.cCap; k += co.n)
+						if (d.cvalid[k] && compat(d.cbits + (long long)k * W, d.cent[k].first, d.cent[k].last, false,
+						                          d.tcb + (long long)j * W, d.tcf[j], d.tcl[j], W) == 1)
+							d.cvalid[k] = 0;
+				}
+			}
+			if (ab < 0) ab = 0;
+			co.sync();
+			if (co.lane == 0) d.tcab[j] = ab;
+			co.sync();
+		}
+		++iterCnt;
+		if (iterCnt >= iterBound) break;
+	}
+	(void)sub;
+	return txCnt;
+}
+
+// CompSortTranscripts (TranscriptDecider.hpp:360-374): ascending first, then the vector WITH the
+// first differing bit first
+PSC_DEV bool tx_row_less(const uint64_t *a, int fa, const uint64_t *b, int fb, int W)
+{
+	if (fa != fb) return fa < fb;
+	for (int w = 0; w < W; ++w)
+		if (a[w] != b[w]) return brev64(a[w]) > brev64(b[w]);
+	return false;
+}
+
+// CoalesceSameTranscripts (TranscriptDecider.cpp:303-328) on the candidate table of component c
+PSC_DEV int dp_coalesce(DpState &st, uint64_t *cb, int *cf, int *cl, int A)
+{
+	const Coop &co = st.co;
+	DpScratch &d = st.d;
+	int W = st.W;
+	if (A <= 1) return A;
+	for (int i = co.lane; i < A; i += co.n) d.sortidx[i] = i;
+	co.sync();
+	coop_sort(co, d.sortidx, A, [&](int a, int b) {
+		if (tx_row_less(cb + (long long)a * W, cf[a], cb + (long long)b * W, cf[b], W)) return true;
+		if (tx_row_less(cb + (long long)b * W, cf[b], cb + (long long)a * W, cf[a], W)) return false;
+		return a < b;
+	});
+	// unique rows -> second buffer, then back
+	int K = 0;
+	for (int b0 = 0; b0 < A; b0 += co.n) {
+		int p = b0 + co.lane;
+		bool head = false;
+		int me = -1;
+		if (p < A) {
+			me = d.sortidx[p];
+			if (p == 0) head = true;
+			else {
+				int pv = d.sortidx[p - 1];
+				head = false;
+				for (int w = 0; w < W; ++w)
+					if (cb[(long long)me * W + w] != cb[(long long)pv * W + w]) { head = true; break; }
+			}
+		}
+		uint32_t m = co.ballot(head);
+		if (head) {
+			int k = K + co.rank_in(m);
+			for (int w = 0; w < W; ++w) d.c2b[(long long)k * W + w] = cb[(long long)me * W + w];
+			d.c2f[k] = cf[me];
+			d.c2l[k] = cl[me];
+		}
+		K += popc32(m);
+	}
+	co.sync();
+	for (int k = co.lane; k < K; k += co.n) {
+		for (int w = 0; w < W; ++w) cb[(long long)k * W + w] = d.c2b[(long long)k * W + w];
+		cf[k] = d.c2f[k];
+		cl[k] = d.c2l[k];
+	}
+	co.sync();
+	return K;
+}
+
+// AugmentTranscripts(limit, extend = false) (TranscriptDecider.cpp:1205-1365)
+PSC_DEV int dp_augment(DpState &st, uint64_t *cb, int *cf, int *cl, int A, int limit, long long cap)
+{
+	const Coop &co = st.co;
+	const CompView &v = st.v;
+	int W = st.W;
+	if (A >= limit) return A;
+	int size = A;
+	bool full = false;
+	co.sync();
+	if (co.lane == 0) {
+		for (int i = 0; i < size && !full; ++i) {
+			const uint64_t *src = cb + (long long)i * W;
+			int tf = cf[i], tl = cl[i];
+			// suffixes starting at a possible start
+			bool firstSeen = false;
+			for (int q = tf; q <= tl && !full; ++q) {
+				if (!bt_test(src, q)) continue;
+				if (!firstSeen) { firstSeen = true; continue; }
+				if (st.cs[q]) {
+					if (A >= cap) { *st.err = 24; full = true; break; }
+					uint64_t *dst = cb + (long long)A * W;
+					for (int w = 0; w < W; ++w) dst[w] = src[w] & keep_mask(w, q, tl);
+					cf[A] = q;
+					cl[A] = tl;
+					++A;
+					if (A >= limit) full = true;
+				}
+			}
+			// prefixes ending at a possible end
+			for (int q = tf; q < tl && !full; ++q) {
+				if (!bt_test(src, q)) continue;
+				if (st.ce[q]) {
+					if (A >= cap) { *st.err = 24; full = true; break; }
+					uint64_t *dst = cb + (long long)A * W;
+					for (int w = 0; w < W; ++w) dst[w] = src[w] & keep_mask(w, tf, q);
+					cf[A] = tf;
+					cl[A] = q;
+					++A;
+					if (A >= limit) full = true;
+				}
+			}
+		}
+	}
+	A = co.bcast(A, 0);
+	full = co.bcast((int)full, 0) != 0;
+	co.sync();
+	if (full) return A; // the reference returns before the final coalesce when the limit is hit
+	return dp_coalesce(st, cb, cf, cl, A);
+}
+
+// The DP branch of Solve (TranscriptDecider.cpp:3139-3265) for component c
+PSC_DEVN void dp_candidates(const Coop &co, const GraphDev &g, const SolveDev &sv, int c, char *scratch, int *order /* [S] */)
+{
+	DpState st;
+	st.co = co;
+	st.v = comp_view(g, c);
+	const CompView &v = st.v;
+	int S = sv.prm.S;
+	int E = v.noff[v.n] - v.noff[0];
+	int Cmax = 0;
+	for (int s = 0; s < S; ++s) {
+		int cc = sv.samples[s].n_con[c];
+		if (cc > Cmax) Cmax = cc;
+	}
+	long long row0 = sv.cand_row_off[c];
+	long long cap = sv.cand_row_off[c + 1] - row0;
+	dp_scratch_layout(&st.d, scratch, v.n, E, Cmax, cap);
+	st.cs = sv.can_start + v.base;
+	st.ce = sv.can_end + v.base;
+	st.W = v.W;
+	st.epoch = 0;
+	st.err = sv.error_flag;
+	st.forAbundance = false;
+	st.minAbundance = 0;
+	st.timeStamp = 0;
+	int W = v.W;
+	uint64_t *cb = sv.cand_bits + sv.cand_bits_off[c];
+	int *cf = sv.cand_first + row0, *cl = sv.cand_last + row0;
+	// samples in ascending number of constraints, stable (Q11), visited from the largest
+	co.sync();
+	if (co.lane == 0) {
+		for (int s = 0; s < S; ++s) order[s] = s;
+		for (int a = 1; a < S; ++a) {
+			int x = order[a], xc = sv.samples[x].n_con[c], b = a - 1;
+			while (b >= 0 && sv.samples[order[b]].n_con[c] > xc) { order[b + 1] = order[b]; --b; }
+			order[b + 1] = x;
+		}
+	}
+	co.sync();
+	int A = 0;
+	int downsampleCnt = -1;
+	for (int oi = S - 1; oi >= 0; --oi) {
+		int s = order[oi];
+		TableView t = table_view(sv.samples[s], c);
+		int iterBound = t.C;
+		if (oi < S - 1) iterBound = 100;
+		if (oi < S - 10 && A > 1000) iterBound = 10;
+		int maxDp = sv.prm.maxDpConstraintSize;
+		int stride = 1;
+		bool skip = false;
+		if (maxDp > 0) {
+			// TruncateConstraintsCoverFrom (Constraints.hpp:400-434)
+			for (int k = co.lane; k < t.C; k += co.n) {
+				const uint64_t *src = t.bits + (long long)k * W;
+				uint64_t *dst = st.d.tcb + (long long)k * W;
+				for (int w = 0; w < W; ++w) dst[w] = 0;
+				int taken = 0, last = t.first[k];
+				for (int q = t.first[k]; q <= t.last[k] && taken < maxDp; ++q)
+					if (bt_test(src, q)) { bt_set(dst, q); last = q; ++taken; }
+				st.d.tcf[k] = t.first[k];
+				st.d.tcl[k] = last;
+				st.d.tcsup[k] = t.support[k];
+				st.d.tcnorm[k] = t.norm[k];
+				st.d.tcab[k] = t.norm[k];
+			}
+			st.d.tcCnt = t.C;
+		} else {
+			bool down = (t.C > 1000 && (long long)t.C * 10 < t.M) || (downsampleCnt > 0 && t.C >= downsampleCnt) || v.n >= 1500;
+			if (down) { // DownsampleConstraintsFrom (Constraints.hpp:362-398)
+				stride = t.C > 0 ? t.M / t.C : 1;
+				if (downsampleCnt > 0) stride = t.C / downsampleCnt;
+				if (stride < 1) stride = 1;
+			}
+			int cnt = down ? (t.C + stride - 1) / stride : t.C;
+			for (int k = co.lane; k < cnt; k += co.n) {
+				int src = k * stride;
+				for (int w = 0; w < W; ++w) st.d.tcb[(long long)k * W + w] = t.bits[(long long)src * W + w];
+				st.d.tcf[k] = t.first[src];
+				st.d.tcl[k] = t.last[src];
+				st.d.tcsup[k] = t.support[src];
+				st.d.tcnorm[k] = t.norm[src];
+				st.d.tcab[k] = t.norm[src];
+			}
+			st.d.tcCnt = cnt;
+			if (down) {
+				if (downsampleCnt <= 0) downsampleCnt = cnt;
+				if (iterBound <= 10) skip = true;
+			}
+		}
+		co.sync();
+		if (skip) continue;
+		int nt = dp_pick(st, iterBound);
+		// PickTranscriptsByDP coalesces its own list before handing it over (.cpp:1166)
+		nt = dp_coalesce(st, st.d.txb, st.d.txf, st.d.txl, nt);
+		if (A + nt > cap) {
+			*st.err = 25;
+			nt = (int)(cap - A);
+		}
+		for (int k = co.lane; k < nt; k += co.n) {
+			for (int w = 0; w < W; ++w) cb[(long long)(A + k) * W + w] = st.d.txb[(long long)k * W + w];
+			cf[A + k] = st.d.txf[k];
+			cl[A + k] = st.d.txl[k];
+		}
+		A += nt;
+		co.sync();
+		A = dp_coalesce(st, cb, cf, cl, A);
+		A = dp_augment(st, cb, cf, cl, A, 1000, cap);
+	}
+	for (int k = co.lane; k < A; k += co.n) {
+		sv.cand_corr[row0 + k] = 0;
+		sv.cand_sup1[row0 + k] = 0;
+		sv.cand_sup2[row0 + k] = 0;
+	}
+	if (co.lane == 0) sv.n_cand[c] = A;
+	co.sync();
+}
+
+} // namespace pscdev

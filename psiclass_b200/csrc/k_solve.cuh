@@ -1,0 +1,779 @@
+// k_solve.cuh -- TranscriptDecider::Solve on the device (TranscriptDecider.cpp:2874-3460).
+//
+// Work units: one cooperative group (Coop, 1 or 32 lanes) per component for the cross-sample
+// steps and per (component, sample) for the per-sample steps; kernel boundaries stand where the
+// reference has its three cross-sample reductions.  All working storage is
+// carved out of per-unit scratch arenas in HBM that the host sizes from the table sizes.
+#pragma once
+#include "psc_internal.h"
+
+namespace pscdev {
+
+#define PSC_USE_DP 200000
+
+struct SolveParams {
+	double fpkmFraction, classifierThreshold, minDepth;
+	int maxDpConstraintSize, S;
+	int readLen, fragLen, fragStdev, matePaired;
+};
+
+// ---- bump allocator used identically by the host (sizing, base == 0) and the device ----
+struct Carver {
+	char *base;
+	size_t off;
+	__host__ __device__ Carver(char *b) : base(b), off(0) {}
+	template <class T> __host__ __device__ T *take(size_t n)
+	{
+		off = (off + 15) & ~(size_t)15;
+		T *p = (T *)(base + off);
+		off += n * sizeof(T);
+		return p;
+	}
+};
+
+// ---- per-component state that persists through the whole solve ----
+struct SolveDev {
+	SolveParams prm;
+	const SampleDev *samples;
+	// prologue results
+	uint8_t *can_start, *can_end; // [n_se]
+	int *edge_support;            // [n_next]  #samples supporting the intron edge (subexonChainSupport)
+	int *cs00;                    // [n_comp]  the {0,0} entry an empty chain list leaves behind
+	int *at_cnt, *use_dp;         // [n_comp]
+	int *def_gene;                // [2*n_comp]
+	// candidate transcripts (alltranscripts)
+	const long long *cand_row_off;  // [n_comp+1]
+	const long long *cand_bits_off; // [n_comp+1] in words
+	int *n_cand;                    // [n_comp]
+	uint64_t *cand_bits;
+	int *cand_first, *cand_last;
+	int8_t *cand_corr;          // correlationScore of the candidate (1 for single-subexon enumerated paths)
+	int *cand_sup1, *cand_sup2; // #samples that picked it in round 1 / kept it after refinement
+	int *error_flag;
+};
+
+// per-unit results that live from the pick kernel to the emit kernel
+struct UnitPred {
+	int *id;
+	double *abundance, *fpkm;
+	int8_t *corr;
+	int *raw_id;
+	double *raw_abundance;
+};
+__host__ __device__ inline size_t unit_pred_layout(UnitPred *o, char *base, int cap)
+{
+	Carver cv(base);
+	int *id = cv.take<int>((size_t)2 * cap);
+	double *ab = cv.take<double>((size_t)2 * cap);
+	double *fp = cv.take<double>((size_t)2 * cap);
+	int8_t *co = cv.take<int8_t>((size_t)2 * cap);
+	int *rid = cv.take<int>((size_t)cap);
+	double *rab = cv.take<double>((size_t)cap);
+	if (o) {
+		o->id = id; o->abundance = ab; o->fpkm = fp; o->corr = co; o->raw_id = rid; o->raw_abundance = rab;
+	}
+	return (cv.off + 15) & ~(size_t)15;
+}
+
+// per-unit scratch of PickTranscripts / AbundanceEstimation / RefineTranscripts
+struct UnitScratch {
+	uint64_t *btable;  // [A * MW]
+	double *tAbund, *avgAbund, *covPortion, *coverCnt, *abund; // [A]
+	double *pairAbund; // [M]
+	int *slot;         // [A] row of the candidate in the csupport pool, -1 if none yet
+	double *pool;      // [cap * M]
+	int *list;         // [A]
+	int *depl;         // [M] pairs depleted in the current iteration
+	uint64_t *tmpbits; // [4 * W]
+	uint8_t *flagsA;   // [max(A, n, C)]  small boolean scratch
+	// EM / refine (T <= 2*cap transcripts)
+	uint64_t *ebtable; // [2*cap * MW]
+	double *rho, *sumj, *dtmp; // [2*cap], [M], [2*cap]
+	int *tlen, *tgid, *icnt; // [2*cap] each
+	double *gMaxFPKM, *gNonOvl, *gMaxCov; // [ng]
+	int *gTag, *gRecover; // [ng]
+	uint8_t *missing; // [E + 1]
+	int *recList;     // [2*cap]
+	uint8_t *used;    // [2*cap]
+};
+__host__ __device__ inline size_t unit_scratch_layout(UnitScratch *o, char *base, int A, int M, int cap, int n, int C,
+                                                      int ng, int E)
+{
+	Carver cv(base);
+	int MW = (M + 63) >> 6, W = (n + 63) >> 6;
+	UnitScratch s;
+	s.btable = cv.take<uint64_t>((size_t)A * MW);
+	s.tAbund = cv.take<double>((size_t)A);
+	s.avgAbund = cv.take<double>((size_t)A);
+	s.covPortion = cv.take<double>((size_t)A);
+	s.coverCnt = cv.take<double>((size_t)A);
+	s.abund = cv.take<double>((size_t)A);
+	s.pairAbund = cv.take<double>((size_t)M);
+	s.slot = cv.take<int>((size_t)A);
+	s.pool = cv.take<double>((size_t)cap * M);
+	s.list = cv.take<int>((size_t)A);
+	s.depl = cv.take<int>((size_t)M + 1);
+	s.tmpbits = cv.take<uint64_t>((size_t)4 * W);
+	int fa = A > n ? A : n;
+	if (C > fa) fa = C;
+	s.flagsA = cv.take<uint8_t>((size_t)fa + 1);
+	s.ebtable = cv.take<uint64_t>((size_t)2 * cap * MW);
+	s.rho = cv.take<double>((size_t)2 * cap);
+	s.sumj = cv.take<double>((size_t)M);
+	s.dtmp = cv.take<double>((size_t)2 * cap);
+	s.tlen = cv.take<int>((size_t)2 * cap);
+	s.tgid = cv.take<int>((size_t)2 * cap);
+	s.icnt = cv.take<int>((size_t)2 * cap);
+	s.gMaxFPKM = cv.take<double>((size_t)ng + 1);
+	s.gNonOvl = cv.take<double>((size_t)ng + 1);
+	s.gMaxCov = cv.take<double>((size_t)ng + 1);
+	s.gTag = cv.take<int>((size_t)ng + 1);
+	s.gRecover = cv.take<int>((size_t)ng + 1);
+	s.missing = cv.take<uint8_t>((size_t)E + 2);
+	s.recList = cv.take<int>((size_t)2 * cap);
+	s.used = cv.take<uint8_t>((size_t)2 * cap + 1);
+	if (o) *o = s;
+	return (cv.off + 15) & ~(size_t)15;
+}
+
+// a chunk of components being processed together
+struct ChunkDev {
+	int c0, c1; // components [c0, c1)
+	const long long *scratch_off; // [(c1-c0)*S + 1] byte offsets into scratch
+	char *scratch;
+	const long long *pred_off; // [(c1-c0)*S + 1] byte offsets into pred
+	char *pred;
+	int *n_pred;      // [(c1-c0)*S]  current size of predTranscripts
+	int *n_raw;       // [(c1-c0)*S]
+	int *n_exon;      // [(c1-c0)*S]  total exons of the final transcripts
+};
+
+// view of one component
+struct CompView {
+	int c, base, n, W;
+	const int *st, *en;
+	const int8_t *lt, *rt, *ls, *rs;
+	const double *lcls, *rcls;
+	const int *gene;
+	const int *noff, *nidx, *poff, *pidx; // noff/poff indexed with local subexon index (already shifted by base)
+	int baseGene, usedGene;
+};
+PSC_DEV CompView comp_view(const GraphDev &g, int c)
+{
+	CompView v;
+	v.c = c;
+	v.base = g.comp_off[c];
+	v.n = g.comp_off[c + 1] - v.base;
+	v.W = (v.n + 63) >> 6;
+	v.st = g.se_start + v.base;
+	v.en = g.se_end + v.base;
+	v.lt = g.lt + v.base;
+	v.rt = g.rt + v.base;
+	v.ls = g.ls + v.base;
+	v.rs = g.rs + v.base;
+	v.lcls = g.lcls + v.base;
+	v.rcls = g.rcls + v.base;
+	v.gene = g.gene + v.base;
+	v.noff = g.next_off + v.base;
+	v.nidx = g.next_idx;
+	v.poff = g.prev_off + v.base;
+	v.pidx = g.prev_idx;
+	v.baseGene = g.comp_base[c];
+	v.usedGene = g.comp_used[c];
+	return v;
+}
+PSC_DEV bool same_strand(int a, int b) { return a == 0 || b == 0 || a == b; }
+
+// view of one (sample, component) constraint table
+struct TableView {
+	int C, M, lo;
+	const uint64_t *bits;
+	const int *first, *last, *support, *uniq;
+	const double *norm;
+	const int *pi, *pj, *psup, *puniq, *pec;
+	const double *pnorm;
+};
+PSC_DEV TableView table_view(const SampleDev &s, int c)
+{
+	TableView t;
+	t.lo = s.grp_lo[c];
+	t.C = s.n_con[c];
+	t.M = s.n_pair[c];
+	t.bits = s.con_bits + s.bits_off[c];
+	t.first = s.con_first + t.lo;
+	t.last = s.con_last + t.lo;
+	t.support = s.con_support + t.lo;
+	t.uniq = s.con_uniq + t.lo;
+	t.norm = s.con_norm + t.lo;
+	t.pi = s.pair_i + t.lo;
+	t.pj = s.pair_j + t.lo;
+	t.psup = s.pair_support + t.lo;
+	t.puniq = s.pair_uniq + t.lo;
+	t.pec = s.pair_ec + t.lo;
+	t.pnorm = s.pair_norm + t.lo;
+	return t;
+}
+
+// =============================================================================================
+// P1: prologue of Solve, one group per component (TranscriptDecider.cpp:2884-3111)
+// =============================================================================================
+PSC_DEV void solve_prologue(const Coop &co, const GraphDev &g, const SolveDev &sv, int c, int *f /* [n] scratch */)
+{
+	CompView v = comp_view(g, c);
+	int n = v.n;
+	uint8_t *cs = sv.can_start + v.base, *ce = sv.can_end + v.base;
+	double thr = sv.prm.classifierThreshold;
+	int S = sv.prm.S;
+	// chain support: every sample marks the intron edges of its well-supported constraints
+	// (.cpp:3005-3064).  Edge marks of one sample are idempotent, so lanes may race on them.
+	int e0 = v.noff[0], e1 = v.noff[n];
+	for (int e = e0 + co.lane; e < e1; e += co.n) sv.edge_support[e] = 0;
+	co.sync();
+	int cs00 = 0;
+	for (int s = 0; s < S; ++s) {
+		TableView t = table_view(sv.samples[s], c);
+		// pass 1: mark (stamp = s + 1 in the high bits would need atomics; use two passes instead)
+		int any = 0;
+		for (int k = co.lane; k < t.C; k += co.n) {
+			if (t.uniq[k] < 0.95 * t.support[k] || t.support[k] < 3) continue;
+			const uint64_t *b = t.bits + (long long)k * v.W;
+			int prev = -1;
+			for (int q = t.first[k]; q <= t.last[k]; ++q) {
+				if (!bt_test(b, q)) continue;
+				if (prev >= 0 && v.en[prev] + 1 < v.st[q]) {
+					any = 1;
+					for (int e = v.noff[prev]; e < v.noff[prev + 1]; ++e)
+						if (v.nidx[e] == q) {
+							// bit 30 marks "seen in the current sample"
+							int old = sv.edge_support[e];
+							if (!(old & (1 << 30))) sv.edge_support[e] = old | (1 << 30);
+							break;
+						}
+				}
+				prev = q;
+			}
+		}
+		any = co.max(any);
+		co.sync();
+		for (int e = e0 + co.lane; e < e1; e += co.n) {
+			int old = sv.edge_support[e];
+			if (old & (1 << 30)) sv.edge_support[e] = (old & ~(1 << 30)) + 1;
+		}
+		co.sync();
+		if (!any) ++cs00; // empty chain: vector::resize(k+1) leaves one {0,0} pair behind (.cpp:3039-3063)
+	}
+	if (co.lane == 0) {
+		sv.cs00[c] = cs00;
+		// start / end flags (.cpp:2884-2973), sequential by nature
+		for (int i = 0; i < n; ++i) {
+			bool st = false, en = false;
+			if (v.poff[i + 1] == v.poff[i]) st = true;
+			else if (v.lcls[i] < thr && v.lcls[i] != -1 && v.ls[i] != 0) st = true; // Q12: the inner test never fires
+			if (v.noff[i + 1] == v.noff[i]) en = true;
+			else if (v.rcls[i] < thr && v.rcls[i] != -1 && v.rs[i] != 0) en = true;
+			cs[i] = st;
+			ce[i] = en;
+			if (en)
+				for (int j = i - 1; j >= 0; --j) {
+					if (v.en[j] + 1 != v.st[j + 1]) break;
+					if (ce[j]) { ce[j] = 0; break; }
+				}
+		}
+		for (int i = 0; i < n;) {
+			int j, k;
+			for (j = i + 1; j < n; ++j)
+				if (v.st[j] > v.en[j - 1] + 1) break;
+			if (!cs[i]) {
+				int cnt[2] = {0, 0};
+				for (k = i; k < j; ++k) {
+					if (!same_strand(v.rs[k], v.ls[i])) break;
+					if (v.ls[k] != 0) ++cnt[(v.ls[k] + 1) / 2];
+				}
+				if (k < j && cnt[(v.rs[k] + 1) / 2] == 0) cs[i] = 1;
+			}
+			if (!ce[j - 1]) {
+				int cnt[2] = {0, 0};
+				for (k = j - 1; k >= i; --k) {
+					if (!same_strand(v.ls[k], v.rs[j - 1])) break;
+					if (v.rs[k] != 0) ++cnt[(v.rs[k] + 1) / 2];
+				}
+				if (k >= i && cnt[(v.ls[k] + 1) / 2] == 0) ce[j - 1] = 1;
+			}
+			i = j;
+		}
+		// default gene ids (.cpp:2979-3003)
+		int d0 = -1, d1 = -1;
+		for (int i = 0; i < n; ++i) {
+			int gid = v.gene[i];
+			if (gid < 0) continue;
+			if ((v.rs[i] == -1 || v.ls[i] == -1) && (d0 == -1 || gid < d0)) d0 = gid;
+			if ((v.rs[i] == 1 || v.ls[i] == 1) && (d1 == -1 || gid < d1)) d1 = gid;
+		}
+		if (d0 == -1) d0 = v.baseGene;
+		if (d1 == -1) d1 = v.usedGene - 1;
+		sv.def_gene[2 * c] = d0;
+		sv.def_gene[2 * c + 1] = d1;
+		// path counts (SubTranscriptCount, .cpp:284-301): int32 wrap-around (Q4); only subexons
+		// reachable from a start are ever visited by the reference's memoised recursion
+		for (int i = 0; i < n; ++i) f[i] = 0; // reach flag first
+		for (int i = 0; i < n; ++i) {
+			if (cs[i]) f[i] = 1;
+			if (f[i])
+				for (int e = v.noff[i]; e < v.noff[i + 1]; ++e) f[v.nidx[e]] = 1;
+		}
+		for (int i = n - 1; i >= 0; --i) {
+			if (!f[i]) { f[i] = -1; continue; }
+			uint32_t r = ce[i] ? 1u : 0u;
+			for (int e = v.noff[i]; e < v.noff[i + 1]; ++e) r += (uint32_t)f[v.nidx[e]];
+			if (r == 0) r = 1;
+			f[i] = (int)r;
+		}
+		uint32_t cnt = 0;
+		for (int i = 0; i < n; ++i)
+			if (cs[i]) cnt += (uint32_t)f[i];
+		int icnt = (int)cnt;
+		bool useDP = false;
+		if (icnt <= PSC_USE_DP) {
+			for (int i = 0; i < n; ++i)
+				if (f[i] > PSC_USE_DP) { useDP = true; break; }
+		} else
+			useDP = true;
+		if (!useDP)
+			for (int s = 0; s < S; ++s) {
+				double msize = (double)sv.samples[s].n_pair[c], csize = (double)sv.samples[s].n_con[c];
+				if (icnt > (csize / msize) * (csize / msize) * n && icnt > PSC_USE_DP / (msize * msize) && icnt > 50) {
+					useDP = true;
+					break;
+				}
+			}
+		sv.at_cnt[c] = icnt;
+		sv.use_dp[c] = useDP ? 1 : 0;
+	}
+	co.sync();
+}
+
+// =============================================================================================
+// P2a: EnumerateTranscript (TranscriptDecider.cpp:330-372): depth-first, in index order
+// =============================================================================================
+PSC_DEV void enumerate_candidates(const Coop &co, const GraphDev &g, const SolveDev &sv, int c, int *stackNode,
+                                  int *stackEdge, int *stackStrand)
+{
+	CompView v = comp_view(g, c);
+	if (co.lane != 0) return;
+	long long row0 = sv.cand_row_off[c];
+	long long cap = sv.cand_row_off[c + 1] - row0;
+	uint64_t *bits = sv.cand_bits + sv.cand_bits_off[c];
+	const uint8_t *cs = sv.can_start + v.base, *ce = sv.can_end + v.base;
+	int W = v.W;
+	long long A = 0;
+	for (int s0 = 0; s0 < v.n; ++s0) {
+		if (!cs[s0]) continue;
+		int depth = 0;
+		stackNode[0] = s0;
+		stackEdge[0] = -1; // -1: node not yet "entered"
+		stackStrand[0] = 0;
+		while (depth >= 0) {
+			int tag = stackNode[depth];
+			if (stackEdge[depth] < 0) {
+				if (ce[tag]) {
+					if (A < cap) {
+						uint64_t *b = bits + A * W;
+						for (int w = 0; w < W; ++w) b[w] = 0;
+						for (int i = 0; i <= depth; ++i) bt_set(b, stackNode[i]);
+						sv.cand_first[row0 + A] = stackNode[0];
+						sv.cand_last[row0 + A] = tag;
+						sv.cand_corr[row0 + A] = depth == 0 ? 1 : 0; // min pairwise correlation: 0 without --ls
+						sv.cand_sup1[row0 + A] = 0;
+						sv.cand_sup2[row0 + A] = 0;
+					} else
+						*sv.error_flag = 11;
+					++A;
+				}
+				stackEdge[depth] = v.noff[tag];
+			}
+			int e = stackEdge[depth];
+			if (e >= v.noff[tag + 1]) {
+				--depth;
+				continue;
+			}
+			stackEdge[depth] = e + 1;
+			int a = v.nidx[e];
+			int strand = stackStrand[depth];
+			bool intron = v.st[a] > v.en[tag] + 1;
+			if (!same_strand(v.rs[tag], strand) && intron) continue;
+			if (intron && strand == 0) strand = v.rs[tag];
+			++depth;
+			stackNode[depth] = a;
+			stackEdge[depth] = -1;
+			stackStrand[depth] = strand;
+		}
+	}
+	sv.n_cand[c] = (int)(A < cap ? A : cap);
+}
+
+// =============================================================================================
+// shared helpers of the per-sample phases
+// =============================================================================================
+PSC_DEV double compute_score(double cnt, double weight, double a, double A, double cor)
+{ // TranscriptDecider.hpp:394-401
+	if (a > A * 0.1) return (cnt * weight) * (1 + pow(a / A, 0.25)) + cor;
+	return (cnt * weight) * (1 + a / A) + cor;
+}
+PSC_DEV int tx_len(const CompView &v, const uint64_t *b, int first, int last)
+{
+	int len = 0;
+	for (int q = first; q <= last; ++q)
+		if (bt_test(b, q)) len += v.en[q] - v.st[q] + 1;
+	return len;
+}
+PSC_DEV double to_fpkm(const SolveParams &p, double abundance, int len)
+{ // ConvertTranscriptAbundanceToFPKM (TranscriptDecider.hpp:405-419), readCnt = 1e6
+	double factor = p.matePaired ? 0.5 : 1;
+	return abundance * factor / ((1000000 / 1000000.0) * (len / 1000.0));
+}
+PSC_DEV int len_from_fpkm(const SolveParams &p, double abundance, double fpkm)
+{ // GetTranscriptLengthFromAbundanceAndFPKM (TranscriptDecider.hpp:421-427)
+	double factor = p.matePaired ? 0.5 : 1;
+	return int(abundance * factor / (fpkm / 1000.0) / (1000000 / 1000000.0) + 0.5);
+}
+PSC_DEV int gene_id_of(const CompView &v, const int *defGene, const uint64_t *b, int first, int last)
+{ // GetTranscriptGeneId (TranscriptDecider.cpp:120-147)
+	if (v.gene[first] != -2) return v.gene[first];
+	if (v.gene[last] != -2) return v.gene[last];
+	for (int q = first; q <= last; ++q)
+		if (bt_test(b, q) && v.gene[q] != -2) return v.gene[q];
+	int prev = -1;
+	for (int q = first; q <= last; ++q) {
+		if (!bt_test(b, q)) continue;
+		if (prev >= 0 && v.en[prev] + 1 < v.st[q]) return defGene[(v.rs[prev] + 1) / 2];
+		prev = q;
+	}
+	return defGene[0];
+}
+
+// candidate transcript accessors
+struct CandView {
+	int A, W;
+	const uint64_t *bits;
+	const int *first, *last;
+	const int8_t *corr;
+	int *sup1, *sup2;
+};
+PSC_DEV CandView cand_view(const SolveDev &sv, int c, int W)
+{
+	CandView k;
+	long long r = sv.cand_row_off[c];
+	k.A = sv.n_cand[c];
+	k.W = W;
+	k.bits = sv.cand_bits + sv.cand_bits_off[c];
+	k.first = sv.cand_first + r;
+	k.last = sv.cand_last + r;
+	k.corr = sv.cand_corr + r;
+	k.sup1 = sv.cand_sup1 + r;
+	k.sup2 = sv.cand_sup2 + r;
+	return k;
+}
+
+// pair j compatible with transcript (both mates): the btable predicate (.cpp:1435-1436)
+PSC_DEV bool pair_in_tx(const TableView &t, int j, const uint64_t *tb, int tf, int tl, int W)
+{
+	int a = t.pi[j], b = t.pj[j];
+	return compat(tb, tf, tl, false, t.bits + (long long)a * W, t.first[a], t.last[a], W) == 1 &&
+	       compat(tb, tf, tl, false, t.bits + (long long)b * W, t.first[b], t.last[b], W) == 1;
+}
+
+// =============================================================================================
+// PickTranscripts (TranscriptDecider.cpp:1368-2119): greedy quantitative set cover
+// round2: candidate weights use the round-1 support (alltranscripts[i].FPKM)
+// output: pr.id / pr.abundance / pr.corr, returns the number picked
+// =============================================================================================
+PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &cd, const TableView &t,
+                             const SolveParams &prm, UnitScratch &sc, int cap, bool round2, UnitPred &pr)
+{
+	int A = cd.A, M = t.M, W = v.W;
+	if (M == 0 || A == 0) return 0;
+	int MW = (M + 63) >> 6;
+	// ---- inf, pair abundances ----
+	double inf = -1;
+	for (int j = co.lane; j < M; j += co.n) {
+		double x = t.support[t.pi[j]];
+		if (t.support[t.pj[j]] > x) x = t.support[t.pj[j]];
+		if (t.pnorm[j] > x) x = t.pnorm[j];
+		if (x > inf) inf = x;
+		sc.pairAbund[j] = t.pnorm[j];
+	}
+	inf = co.max(inf);
+	inf = inf + 1;
+	// ---- compatibility matrix: lanes over pairs, ballot not needed since each lane owns words ----
+	for (long long q = co.lane; q < (long long)A * MW; q += co.n) sc.btable[q] = 0;
+	co.sync();
+	int anySet = 0;
+	for (int i = 0; i < A; ++i) {
+		const uint64_t *tb = cd.bits + (long long)i * W;
+		int tf = cd.first[i], tl = cd.last[i];
+		for (int w = co.lane; w < MW; w += co.n) {
+			uint64_t word = 0;
+			int jend = (w + 1) * 64 < M ? (w + 1) * 64 : M;
+			for (int j = w * 64; j < jend; ++j)
+				if (pair_in_tx(t, j, tb, tf, tl, W)) word |= (uint64_t)1 << (j & 63);
+			sc.btable[(long long)i * MW + w] = word;
+			if (word) anySet = 1;
+		}
+	}
+	anySet = co.max(anySet);
+	co.sync();
+	if (!anySet) return 0;
+
+	// ---- togetherChain regions (.cpp:1481-1517) kept as bit masks in tmpbits: computed on the fly below ----
+	// ---- per-candidate rough abundance: lanes over candidates, sequential over pairs ----
+	double maxAbundance = -1;
+	for (int i = co.lane; i < A; i += co.n) {
+		const uint64_t *tb = cd.bits + (long long)i * W;
+		const uint64_t *bt = sc.btable + (long long)i * MW;
+		int tf = cd.first[i], tl = cd.last[i];
+		double value = inf;
+		int tag = -1;
+		sc.abund[i] = 0;
+		sc.slot[i] = -1;
+		int seIdxCnt = 0;
+		for (int w = 0; w < W; ++w) seIdxCnt += popc64(tb[w]);
+		int compatibleCnt = 0;
+		double avg = 0;
+		for (int j = 0; j < M; ++j) {
+			if (!(bt_test(bt, j) && sc.pairAbund[j] > 0)) continue;
+			++compatibleCnt;
+			double adjust = sc.pairAbund[j];
+			int ci = t.pi[j], cj = t.pj[j];
+			if (seIdxCnt > 1) {
+				int si = t.first[ci] + t.last[ci], sj = t.first[cj] + t.last[cj];
+				bool iEdge = si == 2 * tf || si == 2 * tl;
+				bool jEdge = sj == 2 * tf || sj == 2 * tl;
+				if (ci == cj && iEdge) adjust = inf;
+				else if (ci != cj && iEdge) adjust = t.norm[cj];
+				else if (ci != cj && jEdge) adjust = t.norm[ci];
+			}
+			if (adjust < value) { value = adjust; tag = j; }
+			avg += sc.pairAbund[j];
+		}
+		// covered chains: every consecutive pair of the transcript's subexons must sit together in some
+		// compatible constraint (.cpp:1607-1629, 1660-1673)
+		int cnt = 0;
+		bool uncovered = false;
+		{
+			int prev = -1;
+			for (int q = tf; q <= tl; ++q) {
+				if (!bt_test(tb, q)) continue;
+				if (prev >= 0) {
+					bool cov = false;
+					for (int j = 0; j < M && !cov; ++j) {
+						if (!(bt_test(bt, j) && sc.pairAbund[j] > 0)) continue;
+						const uint64_t *ba = t.bits + (long long)t.pi[j] * W, *bb = t.bits + (long long)t.pj[j] * W;
+						if ((bt_test(ba, prev) && bt_test(ba, q)) || (bt_test(bb, prev) && bt_test(bb, q))) cov = true;
+					}
+					if (cov) ++cnt;
+					else uncovered = true;
+				}
+				prev = q;
+			}
+		}
+		// together penalty (.cpp:1634-1656): regions of >= 2 IR/overhang subexons partially used
+		for (int r0 = 0; r0 < v.n;) {
+			int r1;
+			for (r1 = r0 + 1; r1 < v.n; ++r1)
+				if (v.st[r1] > v.en[r1 - 1] + 1) break;
+			int tot = 0, got = 0;
+			for (int q = r0; q < r1; ++q) {
+				bool tg = (v.lt[q] == 2 && v.rt[q] == 1) || (v.lt[q] == 0 && v.rt[q] == 1) || (v.lt[q] == 2 && v.rt[q] == 0);
+				if (tg) {
+					++tot;
+					if (bt_test(tb, q)) ++got;
+				}
+			}
+			if (tot > 1 && got > 0 && got < tot) value /= 2;
+			r0 = r1;
+		}
+		if (uncovered) value = 0;
+		double portion;
+		if (seIdxCnt > 1) portion = (double)cnt / (double)(seIdxCnt - 1);
+		else portion = 1;
+		if (portion == 0) portion = (double)0.5 / (seIdxCnt);
+		sc.covPortion[i] = portion;
+		if (tag == -1) value = 0;
+		if (value > maxAbundance) maxAbundance = value;
+		sc.tAbund[i] = value;
+		if (tag != -1) avg /= compatibleCnt;
+		sc.avgAbund[i] = avg;
+		sc.coverCnt[i] = -1;
+	}
+	maxAbundance = co.max(maxAbundance);
+	co.sync();
+	if (maxAbundance == 0) {
+		for (int i = co.lane; i < A; i += co.n) sc.tAbund[i] = sc.covPortion[i];
+		maxAbundance = 1;
+		co.sync();
+	}
+	// ---- quantitative set cover (.cpp:1827-2068) ----
+	int poolUsed = 0;
+	for (;;) {
+		// arg-max: lexicographic (score, avgAbund) maximum, lowest index on full ties
+		double bestScore = -1, bestAvg = 0, maxcnt = -1;
+		int bestI = -1;
+		for (int i = co.lane; i < A; i += co.n) {
+			double cnt;
+			if (sc.coverCnt[i] == -1) {
+				const uint64_t *bt = sc.btable + (long long)i * MW;
+				cnt = 0;
+				for (int j = 0; j < M; ++j)
+					if (sc.pairAbund[j] > 0 && bt_test(bt, j)) cnt += t.pec[j];
+				sc.coverCnt[i] = cnt;
+			} else
+				cnt = sc.coverCnt[i];
+			if (cnt < 1) continue;
+			cnt *= sc.covPortion[i];
+			double weight = 1;
+			if (round2 && cd.sup1[i] > 0 && prm.S > 1) weight = (1 + (double)cd.sup1[i] / prm.S);
+			double s = compute_score(cnt, weight, sc.tAbund[i], maxAbundance, (double)cd.corr[i]);
+			if (cnt > maxcnt) maxcnt = cnt;
+			if (bestI == -1 ? (s > bestScore) : (s > bestScore || (s == bestScore && bestAvg < sc.avgAbund[i]))) {
+				bestScore = s;
+				bestAvg = sc.avgAbund[i];
+				bestI = i;
+			}
+		}
+		if (co.n > 1) {
+			maxcnt = co.max(maxcnt);
+			for (int o = 16; o > 0; o >>= 1) {
+				double os = co.bcast(bestScore, co.lane ^ o), oa = co.bcast(bestAvg, co.lane ^ o);
+				int oi = co.bcast(bestI, co.lane ^ o);
+				bool take = false;
+				if (oi >= 0) {
+					if (bestI < 0) take = true;
+					else if (os > bestScore) take = true;
+					else if (os == bestScore) {
+						if (oa > bestAvg) take = true;
+						else if (oa == bestAvg && oi < bestI) take = true;
+					}
+				}
+				if (take) { bestScore = os; bestAvg = oa; bestI = oi; }
+			}
+		}
+		int maxtag = bestI;
+		if (maxcnt == 0 || maxtag == -1) break;
+		const uint64_t *btm = sc.btable + (long long)maxtag * MW;
+		// pair to deplete: smallest remaining abundance, last index on ties (.cpp:1913-1923)
+		double update = inf;
+		int updateTag = 0;
+		{
+			double lu = inf;
+			int lt = -1;
+			for (int j = co.lane; j < M; j += co.n)
+				if (bt_test(btm, j) && sc.pairAbund[j] > 0 && sc.pairAbund[j] <= lu) { lu = sc.pairAbund[j]; lt = j; }
+			if (co.n > 1) {
+				for (int o = 16; o > 0; o >>= 1) {
+					double ou = co.bcast(lu, co.lane ^ o);
+					int ot = co.bcast(lt, co.lane ^ o);
+					if (ot >= 0 && (lt < 0 || ou < lu || (ou == lu && ot > lt))) { lu = ou; lt = ot; }
+				}
+			}
+			if (lt >= 0) { update = lu; updateTag = lt; }
+		}
+		// the chosen candidate needs a csupport row
+		if (sc.slot[maxtag] < 0) {
+			if (poolUsed >= cap) { // cannot happen: one new candidate per iteration, <= M+1 iterations
+				return -1;
+			}
+			double *row = sc.pool + (long long)poolUsed * M;
+			for (int j = co.lane; j < M; j += co.n) row[j] = 0;
+			co.sync();
+			if (co.lane == 0) sc.slot[maxtag] = poolUsed;
+			++poolUsed;
+			co.sync();
+		}
+		double *rowm = sc.pool + (long long)sc.slot[maxtag] * M;
+		int supportCnt = 0, deplCnt = 0;
+		// sequential over pairs: alltranscripts[maxtag].abundance accumulates in index order
+		if (co.lane == 0) {
+			double abm = sc.abund[maxtag];
+			for (int j = 0; j < M; ++j) {
+				if (bt_test(btm, j)) {
+					if (sc.pairAbund[j] > 0) {
+						sc.pairAbund[j] -= 1 * update;
+						double factor = t.pec[j];
+						double tmp = (t.psup[j] * update / t.pnorm[j] * factor);
+						rowm[j] += tmp;
+						abm += tmp;
+						if (sc.pairAbund[j] <= 0) sc.depl[deplCnt++] = j;
+						++supportCnt;
+					} else if (rowm[j] == 0) {
+						double takeOut = 0, factor = t.pec[j];
+						int listCnt = 0;
+						sc.abund[maxtag] = abm;
+						for (int i = 0; i < A; ++i) {
+							if (i == maxtag) continue;
+							if (sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
+								double ci = sc.slot[i] >= 0 ? sc.pool[(long long)sc.slot[i] * M + j] : 0.0;
+								double tmp = (ci + rowm[j]) * sc.tAbund[maxtag] / (sc.tAbund[maxtag] + sc.tAbund[i]) - rowm[j];
+								if (tmp > 0) { sc.list[listCnt++] = i; takeOut += tmp; }
+							}
+						}
+						double ratio = 1, takeOutFactor = 0.5;
+						if (update < t.pnorm[j]) {
+							if (takeOut > (t.psup[j] * update / t.pnorm[j] * factor) * takeOutFactor)
+								ratio = (t.psup[j] * update / t.pnorm[j] * factor) * takeOutFactor / takeOut;
+						} else {
+							if (takeOut > (t.psup[j] * factor) * takeOutFactor)
+								ratio = (t.psup[j] * factor) * takeOutFactor / takeOut;
+						}
+						for (int q = 0; q < listCnt; ++q) {
+							int i = sc.list[q];
+							double *ri = sc.pool + (long long)sc.slot[i] * M; // abund > 0 implies it owns a row
+							double tmp = ((ri[j] + rowm[j]) * sc.tAbund[maxtag] / (sc.tAbund[maxtag] + sc.tAbund[i]) - rowm[j]) * ratio;
+							ri[j] -= tmp;
+							sc.abund[i] -= tmp;
+						}
+						double tmp = takeOut * ratio;
+						rowm[j] += tmp;
+						abm += tmp;
+					}
+				}
+				if (sc.pairAbund[j] < 0) sc.pairAbund[j] = 0;
+			}
+			sc.abund[maxtag] = abm;
+			sc.pairAbund[updateTag] = 0;
+		}
+		supportCnt = co.bcast(supportCnt, 0);
+		deplCnt = co.bcast(deplCnt, 0);
+		co.sync();
+		// coverCnt bookkeeping (.cpp:1965-1973): every candidate sharing a pair that just ran dry
+		for (int i = co.lane; i < A; i += co.n) {
+			const uint64_t *bt = sc.btable + (long long)i * MW;
+			double cc = sc.coverCnt[i];
+			for (int q = 0; q < deplCnt; ++q)
+				if (bt_test(bt, sc.depl[q])) cc -= t.pec[sc.depl[q]];
+			sc.coverCnt[i] = cc;
+		}
+		co.sync();
+		if (supportCnt == 0) break;
+	}
+	// ---- collect (.cpp:2070-2085) ----
+	int T = 0;
+	for (int b0 = 0; b0 < A; b0 += co.n) {
+		int i = b0 + co.lane;
+		bool in = i < A && sc.abund[i] > 0;
+		uint32_t m = co.ballot(in);
+		if (in) {
+			int p = T + co.rank_in(m);
+			pr.id[p] = i;
+			pr.abundance[p] = sc.abund[i];
+			pr.corr[p] = sc.tAbund[i] == 0 ? -1 : 0;
+		}
+		T += popc32(m);
+	}
+	co.sync();
+	return T;
+}
+
+} // namespace pscdev
+
+#include "k_solve2.cuh"
+#include "k_dp.cuh"

@@ -1,0 +1,441 @@
+// psc_api_solve.inl -- host orchestration of Solve: sizing, chunking (the GPU batch scheduler
+// that replaces the worker pool of classes.cpp:318-477), kernel launches and result download.
+// Included at the end of psc_api.cu.
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_prologue(GraphDev g, SolveDev sv, int *fscratch, const int *fs_off, int *counter,
+                                                  int width)
+{
+	Coop co = make_coop(width);
+	for (;;) {
+		int c = 0;
+		if (co.lane == 0) c = atomic_add(counter, 1);
+		c = co.bcast(c, 0);
+		if (c >= g.n_comp) break;
+		solve_prologue(co, g, sv, c, fscratch + fs_off[c]);
+	}
+}
+
+// stack scratch of the enumeration: 3 ints per subexon of the component
+__global__ void __launch_bounds__(128) k_enumerate(GraphDev g, SolveDev sv, const int *list, int nList, int *stk,
+                                                   const int *fs_off, int *counter, int width)
+{
+	Coop co = make_coop(width);
+	for (;;) {
+		int u = 0;
+		if (co.lane == 0) u = atomic_add(counter, 1);
+		u = co.bcast(u, 0);
+		if (u >= nList) break;
+		int c = list[u];
+		int n = g.comp_off[c + 1] - g.comp_off[c];
+		int *b = stk + 3 * (long long)fs_off[c];
+		enumerate_candidates(co, g, sv, c, b, b + n, b + 2 * n);
+		co.sync();
+	}
+}
+
+__global__ void __launch_bounds__(128) k_dp(GraphDev g, SolveDev sv, const int *list, int nList, char *scratch,
+                                            const long long *scr_off, int *order, int *counter, int width)
+{
+	Coop co = make_coop(width);
+	for (;;) {
+		int u = 0;
+		if (co.lane == 0) u = atomic_add(counter, 1);
+		u = co.bcast(u, 0);
+		if (u >= nList) break;
+		dp_candidates(co, g, sv, list[u], scratch + scr_off[u], order + (long long)u * sv.prm.S);
+		co.sync();
+	}
+}
+
+// phase: 1 pick round 1, 2 pick round 2 + filtration, 3 rescue
+__global__ void __launch_bounds__(128) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *order, int *counter,
+                                               int width)
+{
+	Coop co = make_coop(width);
+	int S = sv.prm.S;
+	int nUnits = (ch.c1 - ch.c0) * S;
+	for (;;) {
+		int u = 0;
+		if (co.lane == 0) u = atomic_add(counter, 1);
+		u = co.bcast(u, 0);
+		if (u >= nUnits) break;
+		int ul = order ? order[u] : u;
+		int c = ch.c0 + ul / S, s = ul % S;
+		if (phase == 1) unit_pick_round1(co, g, sv, ch, c, s);
+		else if (phase == 2) unit_pick_round2(co, g, sv, ch, c, s);
+		else unit_rescue(co, g, sv, ch, c, s);
+		co.sync();
+	}
+}
+
+__global__ void __launch_bounds__(128) k_emit(GraphDev g, SolveDev sv, ChunkDev ch, OutDev o, const long long *tx_off,
+                                              const long long *ex_off, int *counter, int width)
+{
+	Coop co = make_coop(width);
+	int S = sv.prm.S;
+	int nUnits = (ch.c1 - ch.c0) * S;
+	for (;;) {
+		int u = 0;
+		if (co.lane == 0) u = atomic_add(counter, 1);
+		u = co.bcast(u, 0);
+		if (u >= nUnits) break;
+		int c = ch.c0 + u / S, s = u % S;
+		unit_emit(co, g, sv, ch, c, s, o, tx_off[u], ex_off[u]);
+		co.sync();
+	}
+}
+
+static int launch_grid(psc_ctx *ctx, long long units)
+{
+	long long groupsPerBlock = 128 / ctx->coop;
+	long long blocks = (units + groupsPerBlock - 1) / groupsPerBlock;
+	long long maxBlocks = (long long)ctx->n_sm * 16;
+	if (blocks > maxBlocks) blocks = maxBlocks;
+	if (blocks < 1) blocks = 1;
+	return (int)blocks;
+}
+
+extern "C" {
+
+int psc_solve(psc_ctx *ctx)
+{
+	cudaSetDevice(ctx->device);
+	if (!ctx->constraints_built) return ctx->fail("psc_build_constraints must run before psc_solve");
+	SolveState &st = ctx->solve;
+	const int S = ctx->prm.n_samples, nc = ctx->gd.n_comp, ns = ctx->gd.n_se;
+	long long launches = 0;
+	CK(cudaEventRecord(ctx->ev0, ctx->stream));
+	st.r_comp.clear(); st.r_sample.clear(); st.r_chr.clear(); st.r_gene.clear(); st.r_strand.clear();
+	st.r_exon_off.assign(1, 0); st.r_exon_start.clear(); st.r_exon_end.clear(); st.r_fpkm.clear(); st.r_cov.clear();
+	st.h_at_cnt.assign((size_t)nc, 0); st.h_use_dp.assign((size_t)nc, 0); st.h_n_cand.assign((size_t)nc, 0);
+	if (nc == 0) {
+		ctx->solved = true;
+		return 0;
+	}
+	int nEdges = 0;
+	for (int c = 0; c < nc; ++c) nEdges += ctx->h_next_cnt[(size_t)c];
+
+	SolveDev sv;
+	memset(&sv, 0, sizeof(sv));
+	sv.prm.fpkmFraction = ctx->prm.fpkm_fraction;
+	sv.prm.classifierThreshold = ctx->prm.classifier_threshold;
+	sv.prm.minDepth = ctx->prm.min_read_depth;
+	sv.prm.maxDpConstraintSize = ctx->prm.max_dp_constraint_size;
+	sv.prm.S = S;
+	sv.prm.readLen = ctx->prm.read_len;
+	sv.prm.fragLen = ctx->prm.frag_len;
+	sv.prm.fragStdev = ctx->prm.frag_stdev;
+	sv.prm.matePaired = ctx->prm.mate_paired;
+	sv.samples = ctx->d_samples.as<SampleDev>();
+
+	std::vector<int> fsOff((size_t)nc + 1);
+	for (int c = 0; c <= nc; ++c) fsOff[(size_t)c] = ctx->h_comp_off[(size_t)c];
+	bool ok = st.can_start.ensure((size_t)ns + 1) && st.can_end.ensure((size_t)ns + 1) &&
+	          st.edge_support.ensure(sizeof(int) * ((size_t)nEdges + 1)) && st.cs00.ensure(sizeof(int) * (size_t)nc) &&
+	          st.at_cnt.ensure(sizeof(int) * (size_t)nc) && st.use_dp.ensure(sizeof(int) * (size_t)nc) &&
+	          st.def_gene.ensure(sizeof(int) * 2 * (size_t)nc) && st.n_cand.ensure(sizeof(int) * (size_t)nc) &&
+	          st.error_flag.ensure(64) && st.fscratch.ensure(sizeof(int) * ((size_t)ns + 1)) &&
+	          upload(ctx, st.fs_off, fsOff.data(), (size_t)nc + 1);
+	if (!ok) return ctx->fail("out of device memory (solve state)");
+	CK(cudaMemsetAsync(st.error_flag.p, 0, 64, ctx->stream));
+	sv.can_start = st.can_start.as<uint8_t>();
+	sv.can_end = st.can_end.as<uint8_t>();
+	sv.edge_support = st.edge_support.as<int>();
+	sv.cs00 = st.cs00.as<int>();
+	sv.at_cnt = st.at_cnt.as<int>();
+	sv.use_dp = st.use_dp.as<int>();
+	sv.def_gene = st.def_gene.as<int>();
+	sv.n_cand = st.n_cand.as<int>();
+	sv.error_flag = st.error_flag.as<int>();
+	int *counter = ctx->d_counter.as<int>();
+
+	// the edge_support array is indexed with the global next-edge index: next_off is global already
+	// ---- P1: prologue ----
+	CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
+	PSC_LAUNCH(k_prologue, launch_grid(ctx, nc), 128, ctx->stream, ctx->gd, sv, st.fscratch.as<int>(), st.fs_off.as<int>(), counter,
+	           ctx->coop);
+	++launches;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(st.h_at_cnt.data(), sv.at_cnt, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(st.h_use_dp.data(), sv.use_dp, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+
+	// ---- candidate capacities ----
+	std::vector<long long> rowOff((size_t)nc + 1), bitsOff((size_t)nc + 1);
+	std::vector<int> enumList, dpList;
+	{
+		long long r = 0, b = 0;
+		for (int c = 0; c < nc; ++c) {
+			int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
+			int W = (n + 63) / 64;
+			long long cap;
+			if (st.h_use_dp[(size_t)c]) {
+				if (n > 10000) return ctx->fail("component with more than 10000 subexons on the DP path is not supported");
+				int Cmax = 0;
+				for (int s = 0; s < S; ++s) Cmax = std::max(Cmax, ctx->samples[(size_t)s].h_ncon[(size_t)c]);
+				cap = 1000 + (long long)Cmax + 100LL * (S - 1) + 8;
+				dpList.push_back(c);
+			} else {
+				cap = std::max(0, st.h_at_cnt[(size_t)c]);
+				enumList.push_back(c);
+			}
+			rowOff[(size_t)c] = r;
+			bitsOff[(size_t)c] = b;
+			r += cap;
+			b += cap * W;
+		}
+		rowOff[(size_t)nc] = r;
+		bitsOff[(size_t)nc] = b;
+		ok = upload(ctx, st.cand_row_off, rowOff.data(), (size_t)nc + 1) && upload(ctx, st.cand_bits_off, bitsOff.data(), (size_t)nc + 1) &&
+		     st.cand_bits.ensure(sizeof(uint64_t) * (size_t)(b + 1)) && st.cand_first.ensure(sizeof(int) * (size_t)(r + 1)) &&
+		     st.cand_last.ensure(sizeof(int) * (size_t)(r + 1)) && st.cand_corr.ensure((size_t)(r + 1)) &&
+		     st.cand_sup1.ensure(sizeof(int) * (size_t)(r + 1)) && st.cand_sup2.ensure(sizeof(int) * (size_t)(r + 1));
+		if (!ok) return ctx->fail("out of device memory (candidate transcripts)");
+	}
+	sv.cand_row_off = st.cand_row_off.as<long long>();
+	sv.cand_bits_off = st.cand_bits_off.as<long long>();
+	sv.cand_bits = st.cand_bits.as<uint64_t>();
+	sv.cand_first = st.cand_first.as<int>();
+	sv.cand_last = st.cand_last.as<int>();
+	sv.cand_corr = st.cand_corr.as<int8_t>();
+	sv.cand_sup1 = st.cand_sup1.as<int>();
+	sv.cand_sup2 = st.cand_sup2.as<int>();
+
+	// ---- P2a: enumeration ----
+	if (!enumList.empty()) {
+		if (!upload(ctx, st.list, enumList.data(), enumList.size()) || !st.stk.ensure(sizeof(int) * 3 * ((size_t)ns + 1)))
+			return ctx->fail("out of device memory");
+		CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
+		// the enumeration is sequential per component: always one thread per unit
+		int saved = ctx->coop;
+		ctx->coop = 1;
+		int grid = launch_grid(ctx, (long long)enumList.size());
+		ctx->coop = saved;
+		PSC_LAUNCH(k_enumerate, grid, 128, ctx->stream, ctx->gd, sv, st.list.as<int>(), (int)enumList.size(), st.stk.as<int>(),
+		           st.fs_off.as<int>(), counter, 1);
+		++launches;
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(ctx->stream)); // enumList staging buffer is reused below
+	}
+	// ---- P2b: DP, in chunks that fit the memory budget ----
+	{
+		size_t i0 = 0;
+		while (i0 < dpList.size()) {
+			std::vector<long long> off;
+			std::vector<std::pair<size_t, size_t>> zero; // (offset, bytes) memo regions
+			long long acc = 0;
+			size_t i1 = i0;
+			while (i1 < dpList.size()) {
+				int c = dpList[i1];
+				int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
+				int Cmax = 0;
+				for (int s = 0; s < S; ++s) Cmax = std::max(Cmax, ctx->samples[(size_t)s].h_ncon[(size_t)c]);
+				long long cap = rowOff[(size_t)c + 1] - rowOff[(size_t)c];
+				size_t need = dp_scratch_layout(nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], Cmax, cap);
+				if (i1 > i0 && (size_t)acc + need > ctx->mem_budget) break;
+				off.push_back(acc);
+				zero.push_back({(size_t)acc, dp_scratch_zero_bytes(n)});
+				acc += (long long)need;
+				++i1;
+			}
+			if (!st.scratch.ensure((size_t)acc + 16)) return ctx->fail("out of device memory (DP scratch)");
+			for (auto &z : zero) CK(cudaMemsetAsync((char *)st.scratch.p + z.first, 0, z.second, ctx->stream));
+			int nList = (int)(i1 - i0);
+			if (!upload(ctx, st.list, dpList.data() + i0, (size_t)nList) || !upload(ctx, st.scr_off, off.data(), off.size()) ||
+			    !st.dp_order.ensure(sizeof(int) * (size_t)nList * S))
+				return ctx->fail("out of device memory");
+			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
+			PSC_LAUNCH(k_dp, launch_grid(ctx, nList), 128, ctx->stream, ctx->gd, sv, st.list.as<int>(), nList, (char *)st.scratch.p,
+			           st.scr_off.as<long long>(), st.dp_order.as<int>(), counter, ctx->coop);
+			++launches;
+			CK(cudaGetLastError());
+			CK(cudaStreamSynchronize(ctx->stream));
+			i0 = i1;
+		}
+	}
+	CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+
+	// ---- P3..P6 per chunk of components ----
+	int c0 = 0;
+	while (c0 < nc) {
+		std::vector<long long> scrOff, predOff;
+		std::vector<long long> cost;
+		long long sAcc = 0, pAcc = 0;
+		int c1 = c0;
+		while (c1 < nc) {
+			int n = ctx->h_comp_off[(size_t)c1 + 1] - ctx->h_comp_off[(size_t)c1];
+			int A = st.h_n_cand[(size_t)c1];
+			long long sNeed = 0, pNeed = 0;
+			std::vector<long long> so((size_t)S), po((size_t)S);
+			for (int s = 0; s < S; ++s) {
+				int M = ctx->samples[(size_t)s].h_npair[(size_t)c1], C = ctx->samples[(size_t)s].h_ncon[(size_t)c1];
+				int cap = std::max(1, std::min(A, M + 1));
+				so[(size_t)s] = sNeed;
+				po[(size_t)s] = pNeed;
+				sNeed += (long long)unit_scratch_layout(nullptr, nullptr, A, M, cap, n, C, ctx->h_comp_ng[(size_t)c1], ctx->h_next_cnt[(size_t)c1]);
+				pNeed += (long long)unit_pred_layout(nullptr, nullptr, cap);
+			}
+			if (c1 > c0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
+			for (int s = 0; s < S; ++s) {
+				scrOff.push_back(sAcc + so[(size_t)s]);
+				predOff.push_back(pAcc + po[(size_t)s]);
+				int M = ctx->samples[(size_t)s].h_npair[(size_t)c1];
+				cost.push_back((long long)A * (M + 1));
+			}
+			sAcc += sNeed;
+			pAcc += pNeed;
+			++c1;
+		}
+		scrOff.push_back(sAcc);
+		predOff.push_back(pAcc);
+		int nUnits = (c1 - c0) * S;
+		std::vector<int> order((size_t)nUnits);
+		for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+		ok = st.scratch.ensure((size_t)sAcc + 16) && st.pred.ensure((size_t)pAcc + 16) &&
+		     upload(ctx, st.scr_off, scrOff.data(), scrOff.size()) && upload(ctx, st.pred_off, predOff.data(), predOff.size()) &&
+		     upload(ctx, st.order, order.data(), order.size()) && st.n_pred.ensure(sizeof(int) * (size_t)nUnits) &&
+		     st.n_raw.ensure(sizeof(int) * (size_t)nUnits) && st.n_exon.ensure(sizeof(int) * (size_t)nUnits);
+		if (!ok) return ctx->fail("out of device memory (unit scratch)");
+		ChunkDev ch;
+		ch.c0 = c0;
+		ch.c1 = c1;
+		ch.scratch_off = st.scr_off.as<long long>();
+		ch.scratch = (char *)st.scratch.p;
+		ch.pred_off = st.pred_off.as<long long>();
+		ch.pred = (char *)st.pred.p;
+		ch.n_pred = st.n_pred.as<int>();
+		ch.n_raw = st.n_raw.as<int>();
+		ch.n_exon = st.n_exon.as<int>();
+		CK(cudaMemsetAsync(ch.n_pred, 0, sizeof(int) * (size_t)nUnits, ctx->stream));
+		CK(cudaMemsetAsync(ch.n_raw, 0, sizeof(int) * (size_t)nUnits, ctx->stream));
+		CK(cudaMemsetAsync(ch.n_exon, 0, sizeof(int) * (size_t)nUnits, ctx->stream));
+		for (int phase = 1; phase <= 3; ++phase) {
+			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
+			PSC_LAUNCH(k_units, launch_grid(ctx, nUnits), 128, ctx->stream, ctx->gd, sv, ch, phase, st.order.as<int>(), counter,
+			           ctx->coop);
+			++launches;
+			CK(cudaGetLastError());
+		}
+		std::vector<int> hPred((size_t)nUnits), hExon((size_t)nUnits);
+		CK(cudaMemcpyAsync(hPred.data(), ch.n_pred, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(hExon.data(), ch.n_exon, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		std::vector<long long> txOff((size_t)nUnits + 1), exOff((size_t)nUnits + 1);
+		long long nt = 0, ne = 0;
+		for (int u = 0; u < nUnits; ++u) {
+			txOff[(size_t)u] = nt;
+			exOff[(size_t)u] = ne;
+			nt += hPred[(size_t)u];
+			ne += hExon[(size_t)u];
+		}
+		txOff[(size_t)nUnits] = nt;
+		exOff[(size_t)nUnits] = ne;
+		if (nt > 0) {
+			ok = upload(ctx, st.tx_off, txOff.data(), txOff.size()) && upload(ctx, st.ex_off, exOff.data(), exOff.size()) &&
+			     st.o_comp.ensure(sizeof(int) * (size_t)nt) && st.o_sample.ensure(sizeof(int) * (size_t)nt) &&
+			     st.o_chr.ensure(sizeof(int) * (size_t)nt) && st.o_gene.ensure(sizeof(int) * (size_t)nt) &&
+			     st.o_strand.ensure((size_t)nt) && st.o_exon_off.ensure(sizeof(long long) * (size_t)nt) &&
+			     st.o_exon_start.ensure(sizeof(int) * (size_t)(ne + 1)) && st.o_exon_end.ensure(sizeof(int) * (size_t)(ne + 1)) &&
+			     st.o_fpkm.ensure(sizeof(double) * (size_t)nt) && st.o_cov.ensure(sizeof(double) * (size_t)nt);
+			if (!ok) return ctx->fail("out of device memory (output)");
+			OutDev o;
+			o.comp = st.o_comp.as<int>();
+			o.sample = st.o_sample.as<int>();
+			o.chr = st.o_chr.as<int>();
+			o.gene = st.o_gene.as<int>();
+			o.strand = st.o_strand.as<int8_t>();
+			o.exon_off = st.o_exon_off.as<long long>();
+			o.exon_start = st.o_exon_start.as<int>();
+			o.exon_end = st.o_exon_end.as<int>();
+			o.fpkm = st.o_fpkm.as<double>();
+			o.cov = st.o_cov.as<double>();
+			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
+			PSC_LAUNCH(k_emit, launch_grid(ctx, nUnits), 128, ctx->stream, ctx->gd, sv, ch, o, st.tx_off.as<long long>(),
+			           st.ex_off.as<long long>(), counter, ctx->coop);
+			++launches;
+			CK(cudaGetLastError());
+			size_t t0 = st.r_comp.size(), e0 = st.r_exon_start.size();
+			st.r_comp.resize(t0 + (size_t)nt); st.r_sample.resize(t0 + (size_t)nt); st.r_chr.resize(t0 + (size_t)nt);
+			st.r_gene.resize(t0 + (size_t)nt); st.r_strand.resize(t0 + (size_t)nt); st.r_fpkm.resize(t0 + (size_t)nt);
+			st.r_cov.resize(t0 + (size_t)nt); st.r_exon_start.resize(e0 + (size_t)ne); st.r_exon_end.resize(e0 + (size_t)ne);
+			std::vector<long long> eo((size_t)nt);
+			CK(cudaMemcpyAsync(st.r_comp.data() + t0, o.comp, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(st.r_sample.data() + t0, o.sample, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(st.r_chr.data() + t0, o.chr, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(st.r_gene.data() + t0, o.gene, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(st.r_strand.data() + t0, o.strand, (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(st.r_fpkm.data() + t0, o.fpkm, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(st.r_cov.data() + t0, o.cov, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(eo.data(), o.exon_off, sizeof(long long) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(st.r_exon_start.data() + e0, o.exon_start, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(st.r_exon_end.data() + e0, o.exon_end, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaStreamSynchronize(ctx->stream));
+			st.r_exon_off.pop_back();
+			for (long long k = 0; k < nt; ++k) st.r_exon_off.push_back((long long)e0 + eo[(size_t)k]);
+			st.r_exon_off.push_back((long long)e0 + ne);
+		}
+		c0 = c1;
+	}
+	int herr = 0;
+	CK(cudaMemcpyAsync(&herr, sv.error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaEventRecord(ctx->ev1, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (herr != 0) return ctx->fail("device-side capacity error " + std::to_string(herr));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+	ctx->timing.solve_ms = ms;
+	ctx->timing.kernel_launches += launches;
+	ctx->solved = true;
+	return 0;
+}
+
+int psc_transcript_counts(psc_ctx *ctx, int64_t *n_transcripts, int64_t *n_exons)
+{
+	if (!ctx->solved) return ctx->fail("psc_solve has not run");
+	*n_transcripts = (int64_t)ctx->solve.r_comp.size();
+	*n_exons = (int64_t)ctx->solve.r_exon_start.size();
+	return 0;
+}
+
+int psc_get_transcripts(psc_ctx *ctx, psc_transcripts *out)
+{
+	if (!ctx->solved) return ctx->fail("psc_solve has not run");
+	SolveState &st = ctx->solve;
+	size_t nt = st.r_comp.size(), ne = st.r_exon_start.size();
+	out->n_transcripts = (int64_t)nt;
+	out->n_exons = (int64_t)ne;
+	if (nt) {
+		memcpy(out->comp, st.r_comp.data(), sizeof(int) * nt);
+		memcpy(out->sample, st.r_sample.data(), sizeof(int) * nt);
+		memcpy(out->chr, st.r_chr.data(), sizeof(int) * nt);
+		memcpy(out->gene_id, st.r_gene.data(), sizeof(int) * nt);
+		memcpy(out->strand, st.r_strand.data(), nt);
+		memcpy(out->fpkm, st.r_fpkm.data(), sizeof(double) * nt);
+		memcpy(out->cov, st.r_cov.data(), sizeof(double) * nt);
+	}
+	for (size_t k = 0; k <= nt; ++k) out->exon_off[k] = (int64_t)st.r_exon_off[k];
+	if (ne) {
+		memcpy(out->exon_start, st.r_exon_start.data(), sizeof(int) * ne);
+		memcpy(out->exon_end, st.r_exon_end.data(), sizeof(int) * ne);
+	}
+	return 0;
+}
+
+int psc_get_comp_stats(psc_ctx *ctx, psc_comp_stats *out)
+{
+	if (!ctx->solved) return ctx->fail("psc_solve has not run");
+	size_t nc = (size_t)ctx->gd.n_comp;
+	if (nc) {
+		memcpy(out->at_cnt, ctx->solve.h_at_cnt.data(), sizeof(int) * nc);
+		memcpy(out->use_dp, ctx->solve.h_use_dp.data(), sizeof(int) * nc);
+		memcpy(out->n_candidates, ctx->solve.h_n_cand.data(), sizeof(int) * nc);
+	}
+	return 0;
+}
+
+} // extern "C"
