@@ -137,6 +137,11 @@ typedef struct psc_timing {
 	double constraints_ms, solve_ms;
 	int64_t kernel_launches;
 	int64_t constraint_bytes; /* algorithmic bytes of the constraint kernel, last call */
+	/* per-kernel device time (CUDA events around every launch, summed) and launch counts of the last
+	 * psc_build_constraints + psc_solve: 0 group_ranges, 1 build_constraints, 2 prologue,
+	 * 3 enumerate, 4 dp, 5 units (pick/refine/EM/rescue), 6 emit, 7 unused */
+	double kernel_ms[8];
+	int64_t kernel_count[8];
 } psc_timing;
 int psc_get_timing(psc_ctx *ctx, psc_timing *out);
 

@@ -136,12 +136,49 @@ struct psc_ctx {
 	SolveState solve;
 
 	psc_timing timing;
+	// per-launch CUDA events (resolved at the next synchronisation point)
+	std::vector<cudaEvent_t> evPool;
+	std::vector<int> evIds;
+	size_t evUsed = 0;
+	void ktime_begin(int id)
+	{
+		if (evUsed + 2 > evPool.size()) {
+			evPool.resize(evUsed + 2);
+			cudaEventCreate(&evPool[evUsed]);
+			cudaEventCreate(&evPool[evUsed + 1]);
+		}
+		evIds.push_back(id);
+		cudaEventRecord(evPool[evUsed], stream);
+	}
+	void ktime_end()
+	{
+		cudaEventRecord(evPool[evUsed + 1], stream);
+		evUsed += 2;
+	}
+	void ktime_collect() // call after a stream synchronisation
+	{
+		for (size_t k = 0; k < evIds.size(); ++k) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, evPool[2 * k], evPool[2 * k + 1]);
+			timing.kernel_ms[evIds[k]] += ms;
+			timing.kernel_count[evIds[k]] += 1;
+		}
+		evIds.clear();
+		evUsed = 0;
+	}
 	int fail(const std::string &m)
 	{
 		err = m;
 		return 1;
 	}
 };
+
+#define KLAUNCH(id, kernel, grid, block, ...)                      \
+	do {                                                            \
+		ctx->ktime_begin(id);                                        \
+		PSC_LAUNCH(kernel, grid, block, ctx->stream, __VA_ARGS__);   \
+		ctx->ktime_end();                                            \
+	} while (0)
 
 #define CK(call)                                                                                   \
 	do {                                                                                            \
@@ -195,6 +232,7 @@ void psc_destroy(psc_ctx *ctx)
 	                 &ctx->d_order, &ctx->d_counter};
 	for (DevBuf *b : all) b->release();
 	ctx->solve.release();
+	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	cudaStreamDestroy(ctx->stream);
@@ -339,6 +377,8 @@ int psc_build_constraints(psc_ctx *ctx)
 		if (!s.loaded) return ctx->fail("psc_set_reads missing for a sample");
 	CK(cudaEventRecord(ctx->ev0, ctx->stream));
 	long long launches = 0;
+	memset(ctx->timing.kernel_ms, 0, sizeof(ctx->timing.kernel_ms));
+	memset(ctx->timing.kernel_count, 0, sizeof(ctx->timing.kernel_count));
 	// ---- K0: group ranges ----
 	for (int si = 0; si < S; ++si) {
 		SampleState &s = ctx->samples[(size_t)si];
@@ -382,7 +422,7 @@ int psc_build_constraints(psc_ctx *ctx)
 		d.pair_ec = s.pair_ec.as<int>();
 		d.pair_norm = s.pair_norm.as<double>();
 		if (nc > 0) {
-			PSC_LAUNCH(k_group_ranges, (nc + 255) / 256, 256, ctx->stream, ctx->gd, d);
+			KLAUNCH(0, k_group_ranges, (nc + 255) / 256, 256, ctx->gd, d);
 			++launches;
 		}
 	}
@@ -438,8 +478,8 @@ int psc_build_constraints(psc_ctx *ctx)
 	if (nUnits > 0) {
 		int block = 128;
 		int grid = ctx->n_sm * 16;
-		PSC_LAUNCH(k_build_constraints, grid, block, ctx->stream, ctx->gd, ctx->d_samples.as<SampleDev>(), S,
-		           ctx->d_order.as<int>(), nUnits, ctx->d_counter.as<int>(), ctx->prm.primary_as_unique, ctx->coop);
+		KLAUNCH(1, k_build_constraints, grid, block, ctx->gd, ctx->d_samples.as<SampleDev>(), S, ctx->d_order.as<int>(), nUnits,
+		        ctx->d_counter.as<int>(), ctx->prm.primary_as_unique, ctx->coop);
 		++launches;
 	}
 	CK(cudaGetLastError());
@@ -454,6 +494,7 @@ int psc_build_constraints(psc_ctx *ctx)
 	CK(cudaStreamSynchronize(ctx->stream)); // also keeps hs/order alive until the copies are done
 	float ms = 0;
 	cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+	ctx->ktime_collect();
 	for (int si = 0; si < S; ++si) {
 		SampleState &s = ctx->samples[(size_t)si];
 		for (int c = 0; c < nc; ++c) {

@@ -155,8 +155,7 @@ int psc_solve(psc_ctx *ctx)
 	// the edge_support array is indexed with the global next-edge index: next_off is global already
 	// ---- P1: prologue ----
 	CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-	PSC_LAUNCH(k_prologue, launch_grid(ctx, nc), 128, ctx->stream, ctx->gd, sv, st.fscratch.as<int>(), st.fs_off.as<int>(), counter,
-	           ctx->coop);
+	KLAUNCH(2, k_prologue, launch_grid(ctx, nc), 128, ctx->gd, sv, st.fscratch.as<int>(), st.fs_off.as<int>(), counter, ctx->coop);
 	++launches;
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(st.h_at_cnt.data(), sv.at_cnt, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
@@ -214,8 +213,8 @@ int psc_solve(psc_ctx *ctx)
 		ctx->coop = 1;
 		int grid = launch_grid(ctx, (long long)enumList.size());
 		ctx->coop = saved;
-		PSC_LAUNCH(k_enumerate, grid, 128, ctx->stream, ctx->gd, sv, st.list.as<int>(), (int)enumList.size(), st.stk.as<int>(),
-		           st.fs_off.as<int>(), counter, 1);
+		KLAUNCH(3, k_enumerate, grid, 128, ctx->gd, sv, st.list.as<int>(), (int)enumList.size(), st.stk.as<int>(), st.fs_off.as<int>(),
+		        counter, 1);
 		++launches;
 		CK(cudaGetLastError());
 		CK(cudaStreamSynchronize(ctx->stream)); // enumList staging buffer is reused below
@@ -248,8 +247,8 @@ int psc_solve(psc_ctx *ctx)
 			    !st.dp_order.ensure(sizeof(int) * (size_t)nList * S))
 				return ctx->fail("out of device memory");
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			PSC_LAUNCH(k_dp, launch_grid(ctx, nList), 128, ctx->stream, ctx->gd, sv, st.list.as<int>(), nList, (char *)st.scratch.p,
-			           st.scr_off.as<long long>(), st.dp_order.as<int>(), counter, ctx->coop);
+			KLAUNCH(4, k_dp, launch_grid(ctx, nList), 128, ctx->gd, sv, st.list.as<int>(), nList, (char *)st.scratch.p,
+			        st.scr_off.as<long long>(), st.dp_order.as<int>(), counter, ctx->coop);
 			++launches;
 			CK(cudaGetLastError());
 			CK(cudaStreamSynchronize(ctx->stream));
@@ -316,8 +315,7 @@ int psc_solve(psc_ctx *ctx)
 		CK(cudaMemsetAsync(ch.n_exon, 0, sizeof(int) * (size_t)nUnits, ctx->stream));
 		for (int phase = 1; phase <= 3; ++phase) {
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			PSC_LAUNCH(k_units, launch_grid(ctx, nUnits), 128, ctx->stream, ctx->gd, sv, ch, phase, st.order.as<int>(), counter,
-			           ctx->coop);
+			KLAUNCH(5, k_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, ch, phase, st.order.as<int>(), counter, ctx->coop);
 			++launches;
 			CK(cudaGetLastError());
 		}
@@ -355,8 +353,8 @@ int psc_solve(psc_ctx *ctx)
 			o.fpkm = st.o_fpkm.as<double>();
 			o.cov = st.o_cov.as<double>();
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			PSC_LAUNCH(k_emit, launch_grid(ctx, nUnits), 128, ctx->stream, ctx->gd, sv, ch, o, st.tx_off.as<long long>(),
-			           st.ex_off.as<long long>(), counter, ctx->coop);
+			KLAUNCH(6, k_emit, launch_grid(ctx, nUnits), 128, ctx->gd, sv, ch, o, st.tx_off.as<long long>(), st.ex_off.as<long long>(),
+			        counter, ctx->coop);
 			++launches;
 			CK(cudaGetLastError());
 			size_t t0 = st.r_comp.size(), e0 = st.r_exon_start.size();
@@ -388,6 +386,7 @@ int psc_solve(psc_ctx *ctx)
 	if (herr != 0) return ctx->fail("device-side capacity error " + std::to_string(herr));
 	float ms = 0;
 	cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+	ctx->ktime_collect();
 	ctx->timing.solve_ms = ms;
 	ctx->timing.kernel_launches += launches;
 	ctx->solved = true;
