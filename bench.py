@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- stage-3 throughput: subexon-graph components assembled per second (all samples).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA engine (libpsc.so)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU `classes`
+
+Workload (BASELINE.json configs[1]): seeded synthetic 10-sample human-scale subexon graph
+(~57k components from 60k gene models on 24 contigs, ~60 read pairs / component / sample), stage 3
+only.  One "step" = one full pass of the hot path over the whole batch:
+
+  value : psc_build_constraints + psc_solve with graph and alignment records resident in HBM
+  e2e   : psc_set_reads (pinned host -> device) + build + solve + psc_get_transcripts (device -> host)
+
+With N > 1 (torchrun, one rank per GPU) every rank processes its own workload of the same size
+(weak scaling, no data-path collective); the time is the max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(seed=1001, n_chr=24, n_genes=60000, n_samples=10, mean_pairs=60.0)
+CPU_SAMPLE = dict(seed=1001, n_chr=24, n_genes=1500, n_samples=10, mean_pairs=60.0)
+METRIC = "subexon-graph components assembled/sec (stage 3, all samples)"
+UNIT = "components/s"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of the profiling recipe, sampled during the timed region."""
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        # under load == the upper half of the samples
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference_cpu(cfg, steps, warmup, cores):
+    """Times the unmodified reference `classes` (oracle/_ref, built from /root/reference) on a bounded
+    sample of the workload, on all host cores (-p cores)."""
+    from psiclass_b200 import testkit
+    ref = os.path.join(testkit.REF_DIR, "classes")
+    kind = "reference"
+    if not os.path.exists(ref):
+        ref = os.path.join(testkit.REF_DIR, "psc_oracle")  # the CPU restatement
+        kind = "port"
+    if not os.path.exists(ref):
+        return None
+    wl = testkit.Workload.synth(threads=cores, **cfg)
+    d = tempfile.mkdtemp(prefix="psc_bench_")
+    try:
+        wl.write_files(d)
+        ncomp = wl.n_comp
+        # warm the page cache
+        for f in os.listdir(d):
+            with open(os.path.join(d, f), "rb") as fh:
+                while fh.read(1 << 24):
+                    pass
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            cmd = [ref, "--lb", os.path.join(d, "bamlist"), "-s", os.path.join(d, "subexon_combined.out"),
+                   "-o", os.path.join(d, "out"), "-p", str(cores if kind == "reference" else 1)]
+            subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        mean = sum(times) / len(times)
+        return {"value": ncomp / mean, "unit": UNIT, "cores": cores if kind == "reference" else 1, "kind": kind,
+                "sample": "%d components x %d samples (same generator and seed as the workload, %d gene models), "
+                          "BAM files on local disk, page cache warm, `classes -p %d`, %.2f s per pass"
+                          % (ncomp, cfg["n_samples"], cfg["n_genes"], cores, mean),
+                "seconds_per_pass": mean}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="psc")
+    ap.add_argument("--genes", type=int, default=None, help="override the number of gene models (debugging)")
+    ap.add_argument("--coop", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = host_cores()
+    cfg = dict(WORKLOAD)
+    cpu_cfg = dict(CPU_SAMPLE)
+    if a.genes:
+        cfg["n_genes"] = a.genes
+        cpu_cfg["n_genes"] = min(a.genes, cpu_cfg["n_genes"])
+    config = {"workload": "synthetic 10-sample human-scale subexon graph, stage 3 only (BASELINE.json configs[1]): "
+                          "%d gene models on %d contigs, seed %d, %d samples, ~%d read pairs/component/sample"
+                          % (cfg["n_genes"], cfg["n_chr"], cfg["seed"], cfg["n_samples"], int(cfg["mean_pairs"])),
+              "l2": "inputs (alignment records + tables, several GB per GPU) are far larger than the 126 MB L2",
+              "sharding": "each rank assembles its own workload of this size (by component, no collective)"}
+
+    # ------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        warm = max(0, min(a.warmup, 1))
+        r = run_reference_cpu(cpu_cfg, a.steps, warm, cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built"}))
+            return 0
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": warm, "ms_per_step": 1000.0 * r["seconds_per_pass"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+u64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ CUDA arm
+    import torch
+    from psiclass_b200 import abi, testkit
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg_rank = dict(cfg)
+    cfg_rank["seed"] = cfg["seed"] + 7919 * rank
+    wl = testkit.Workload.synth(threads=max(1, cores // max(1, world)), **cfg_rank)
+    S, ncomp = wl.n_samples, wl.n_comp
+    eng = abi.Engine(device=local_rank)
+    prm = wl.params()
+    eng.call("psc_set_params", C.byref(prm))
+    eng.call("psc_set_coop_width", a.coop)
+    g = wl.graph()
+    eng.call("psc_set_graph", C.byref(g))
+    reads = [wl.reads(s) for s in range(S)]
+    # pin the host copies of the alignment records (the H2D source of the e2e path)
+    cudart = torch.cuda.cudart()
+    h2d = 0
+    for r in reads:
+        n, ns = r.n_reads, r.n_segs
+        for ptr, nbytes in ((r.pos, 4 * n), (r.mate_pos, 4 * n), (r.flags, n), (r.nh, n), (r.name_key, 8 * n),
+                            (r.seg_off, 4 * (n + 1)), (r.seg_a, 4 * ns), (r.seg_b, 4 * ns)):
+            if nbytes:
+                cudart.cudaHostRegister(C.cast(ptr, C.c_void_p).value, nbytes, 0)
+            h2d += nbytes
+
+    def upload():
+        for s in range(S):
+            eng.call("psc_set_reads", s, C.byref(reads[s]))
+
+    out_bufs = {}
+
+    def download():
+        nt, ne = C.c_int64(), C.c_int64()
+        eng.call("psc_transcript_counts", C.byref(nt), C.byref(ne))
+        nt, ne = nt.value, ne.value
+        if out_bufs.get("cap", (0, 0)) < (nt, ne):
+            import numpy as np
+            out_bufs["cap"] = (nt, ne)
+            out_bufs["arrs"] = [np.empty(nt + 1, np.int32) for _ in range(4)] + [np.empty(nt + 1, np.int8)] + \
+                [np.empty(nt + 2, np.int64)] + [np.empty(ne + 1, np.int32) for _ in range(2)] + \
+                [np.empty(nt + 1, np.float64) for _ in range(2)]
+        arrs = out_bufs["arrs"]
+        t = abi.psc_transcripts()
+        t.comp, t.sample, t.chr, t.gene_id = [x.ctypes.data_as(abi.i32p) for x in arrs[0:4]]
+        t.strand = arrs[4].ctypes.data_as(abi.i8p)
+        t.exon_off = arrs[5].ctypes.data_as(abi.i64p)
+        t.exon_start, t.exon_end = [x.ctypes.data_as(abi.i32p) for x in arrs[6:8]]
+        t.fpkm, t.cov = [x.ctypes.data_as(abi.f64p) for x in arrs[8:10]]
+        eng.call("psc_get_transcripts", C.byref(t))
+        return nt, nt * 34 + ne * 8
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        eng.call("psc_build_constraints")
+        eng.call("psc_solve")
+
+    def step_e2e():
+        upload()
+        eng.call("psc_build_constraints")
+        eng.call("psc_solve")
+        return download()
+
+    upload()
+    for _ in range(a.warmup):
+        step_resident()
+    # ---- timed: inputs resident ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms, kms, kcnt, kbytes, launches = 0.0, [0.0] * 8, [0] * 8, [0] * 8, 0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_resident()
+        tm = eng.timing()
+        dev_ms += tm.constraints_ms + tm.solve_ms
+        launches += tm.kernel_launches
+        for k in range(8):
+            kms[k] += tm.kernel_ms[k]
+            kcnt[k] += tm.kernel_count[k]
+            kbytes[k] = tm.kernel_bytes[k]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # the step includes small host-side sizing passes between launches, so the step time is the
+    # synchronised wall time around the K steps (device events cover the kernels only)
+    t_res = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+    wall_max = float(t_res.item())
+    # ---- timed: end to end through the C ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    ntx = 0
+    for _ in range(a.steps):
+        ntx, d2h = step_e2e()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_max = float(t_e.item())
+    tot_comp = torch.tensor([float(ncomp)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tot_comp, op=dist.ReduceOp.SUM)
+    total_components = float(tot_comp.item())
+
+    if rank == 0:
+        names = ["group_ranges", "build_constraints", "prologue", "enumerate", "dp", "units", "emit", "-"]
+        dom = max(range(8), key=lambda k: kms[k])
+        peak, peak_src = measured_peak()
+        per_launch_ms = kms[dom] / max(1, kcnt[dom])
+        # algorithmic bytes are modelled per step for kernels 1 and 5; per launch = per step / launches per step
+        launches_per_step = max(1, kcnt[dom] // max(1, a.steps))
+        alg = kbytes[dom] / launches_per_step
+        achieved = (alg / 1e9) / (per_launch_ms / 1e3) if per_launch_ms > 0 and alg > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": total_components * a.steps / wall_max, "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * wall_max / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+u64",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": total_components * a.steps / e2e_max, "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_" + names[dom], "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "ms_per_launch": per_launch_ms},
+            "kernel_ms_per_step": {names[k]: kms[k] / a.steps for k in range(8) if kcnt[k]},
+            "device_ms_per_step": dev_ms / a.steps,
+            "components_per_rank": ncomp, "transcripts_per_rank": int(ntx),
+            "reads_per_rank": int(sum(r.n_reads for r in reads)),
+        }
+        if not a.no_cpu_baseline and world >= 1:
+            try:
+                r = run_reference_cpu(cpu_cfg, 1, 0, cores)
+                if r:
+                    line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": "failed: %s" % e}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

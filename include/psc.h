@@ -142,6 +142,7 @@ typedef struct psc_timing {
 	 * 3 enumerate, 4 dp, 5 units (pick/refine/EM/rescue), 6 emit, 7 unused */
 	double kernel_ms[8];
 	int64_t kernel_count[8];
+	int64_t kernel_bytes[8]; /* algorithmic bytes attributed to the kernel, 0 if not modelled */
 } psc_timing;
 int psc_get_timing(psc_ctx *ctx, psc_timing *out);
 

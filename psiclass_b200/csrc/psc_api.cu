@@ -379,6 +379,7 @@ int psc_build_constraints(psc_ctx *ctx)
 	long long launches = 0;
 	memset(ctx->timing.kernel_ms, 0, sizeof(ctx->timing.kernel_ms));
 	memset(ctx->timing.kernel_count, 0, sizeof(ctx->timing.kernel_count));
+	memset(ctx->timing.kernel_bytes, 0, sizeof(ctx->timing.kernel_bytes));
 	// ---- K0: group ranges ----
 	for (int si = 0; si < S; ++si) {
 		SampleState &s = ctx->samples[(size_t)si];
@@ -505,6 +506,7 @@ int psc_build_constraints(psc_ctx *ctx)
 	ctx->timing.constraints_ms = ms;
 	ctx->timing.kernel_launches = launches;
 	ctx->timing.constraint_bytes = algBytes;
+	ctx->timing.kernel_bytes[1] = algBytes;
 	ctx->constraints_built = true;
 	ctx->solved = false;
 	return 0;

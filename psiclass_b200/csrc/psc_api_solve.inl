@@ -387,6 +387,23 @@ int psc_solve(psc_ctx *ctx)
 	float ms = 0;
 	cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
 	ctx->ktime_collect();
+	{
+		// algorithmic bytes of the per-unit kernels: the constraint + pair tables are read
+		// once, the compatibility bit-matrix is written and read once, the picked transcripts written once
+		long long bytes = 0;
+		for (int c = 0; c < nc; ++c) {
+			int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
+			int W = (n + 63) / 64;
+			long long A = st.h_n_cand[(size_t)c];
+			bytes += 48LL * n + 8LL * ctx->h_next_cnt[(size_t)c] + A * (8LL * W + 16);
+			for (int s = 0; s < S; ++s) {
+				long long C = ctx->samples[(size_t)s].h_ncon[(size_t)c], M = ctx->samples[(size_t)s].h_npair[(size_t)c];
+				bytes += C * (8LL * W + 40) + M * 24 + 2 * ((A * M + 7) / 8);
+			}
+		}
+		bytes += (long long)st.r_comp.size() * 40 + (long long)st.r_exon_start.size() * 8;
+		ctx->timing.kernel_bytes[5] = bytes;
+	}
 	ctx->timing.solve_ms = ms;
 	ctx->timing.kernel_launches += launches;
 	ctx->solved = true;

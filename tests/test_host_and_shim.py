@@ -1,0 +1,83 @@
+"""Host logic (BAM reader/writer, graph flattening, sharding, Q8, GTF writer) and the kernel LOGIC
+compiled for the CPU by tests/shim (one-lane serial build of the same .cu sources).  These are
+debugging / host-logic tests: they say nothing about the CUDA path, which the -m gpu tests cover."""
+import os
+
+import pytest
+
+from conftest import ROOT, gtf_body, run, stage_fixture
+from psiclass_b200 import testkit
+
+CLASSES_SHIM = os.path.join(ROOT, "tests", "shim", "_build", "classes_shim")
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=41, n_genes=50, n_samples=3),
+    dict(seed=42, n_genes=30, n_samples=4, mean_pairs=200.0, exon_mu=2.2, iso_lambda=4.0, p_alt=0.3, p_ir=0.1),
+    dict(seed=43, n_genes=40, n_samples=2, single_end=1),
+    dict(seed=44, n_genes=40, n_samples=5, p_paralog=0.15, stranded=1, name_style=2, p_noise=0.1, p_overlap=0.15),
+])
+def test_kernel_logic_matches_oracle_on_cpu_shim(cfg):
+    wl = testkit.Workload.synth(threads=4, **cfg)
+    rep = wl.check(testkit.SHIM_PATH, coop=1)
+    assert rep.passed, rep.summary()
+    assert rep.tables_checked == wl.n_comp * wl.n_samples and rep.val_close == 0
+
+
+def test_unlimited_dp_constraints_and_paralog_flag():
+    wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=4)
+    assert wl.check(testkit.SHIM_PATH, coop=1, max_dp=-1).passed
+    assert wl.check(testkit.SHIM_PATH, coop=1, primary_paralog=1).passed
+
+
+def test_bam_roundtrip_equals_direct_records(tmp_path):
+    """Records pushed straight through the filter == records decoded from the BAM the writer made."""
+    wl = testkit.Workload.synth(seed=46, n_genes=30, n_samples=2, name_style=2, p_noise=0.15, threads=2)
+    d = str(tmp_path)
+    wl.write_files(d)
+    w2 = testkit.Workload.load(d)
+    assert w2.n_comp == wl.n_comp
+    import ctypes as C
+    for s in range(wl.n_samples):
+        a, b = wl.reads(s), w2.reads(s)
+        assert a.n_reads == b.n_reads and a.n_segs == b.n_segs and a.read_len == b.read_len and a.frag_stdev == b.frag_stdev
+        n, ns = a.n_reads, a.n_segs
+        for fa, fb, k in ((a.pos, b.pos, n), (a.mate_pos, b.mate_pos, n), (a.flags, b.flags, n), (a.nh, b.nh, n),
+                          (a.name_key, b.name_key, n), (a.seg_off, b.seg_off, n + 1), (a.seg_a, b.seg_a, ns), (a.seg_b, b.seg_b, ns)):
+            assert fa[:k] == fb[:k]
+        assert testkit.lib().tk_total_read_cnt(wl.h, s) == testkit.lib().tk_total_read_cnt(w2.h, s)
+
+
+@pytest.mark.parametrize("name", ["synth_small", "dp_small"])
+@pytest.mark.parametrize("shards", [1, 3])
+def test_front_end_reproduces_reference_gtfs(name, shards, tmp_path):
+    """argv handling, single-pass BAM decode, component sharding, Q8 and the GTF writer: the drop-in
+    `classes` (linked against the shim here) must print the reference's GTF bodies byte for byte."""
+    d = stage_fixture(name, tmp_path)
+    env = dict(os.environ, PSC_GPUS=str(shards))
+    out = run([CLASSES_SHIM, "--lb", "bamlist", "-s", "subexon_combined.out", "-o", "new", "-p", "3"], cwd=d, env=env)
+    n = len(open(os.path.join(d, "bamlist")).read().split())
+    for s in range(n):
+        assert gtf_body(os.path.join(d, "new_sample_%d.gtf" % s)) == gtf_body(os.path.join(d, "ref_sample_%d.gtf" % s))
+    golden = [ln for ln in open(os.path.join(d, "ref_dump.txt")).read().splitlines() if "atCnt=" in ln]
+    assert [ln for ln in out.splitlines() if "atCnt=" in ln] == golden
+
+
+def test_front_end_error_paths(tmp_path):
+    import subprocess
+    r = subprocess.run([CLASSES_SHIM], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "Required:" in r.stdout            # classes.cpp:102-106
+    r = subprocess.run([CLASSES_SHIM, "-b", "x.bam"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1 and "Cannot find combined subexon file." in r.stdout   # classes.cpp:210-214
+    r = subprocess.run([CLASSES_SHIM, "--nonsense"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1                                        # classes.cpp:204-208
+    d = stage_fixture("synth_small", tmp_path)
+    r = subprocess.run([CLASSES_SHIM, "-s", "subexon_combined.out"], cwd=d, stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Must use -b option" in r.stdout   # classes.cpp:215-219
+
+
+def test_empty_and_ragged_inputs():
+    # a sample with (almost) no reads, genes without reads, single-subexon genes
+    wl = testkit.Workload.synth(seed=47, n_genes=30, n_samples=3, mean_pairs=0.3, exon_min=1, exon_max=2, threads=2)
+    rep = wl.check(testkit.SHIM_PATH, coop=1)
+    assert rep.passed, rep.summary()
