@@ -312,7 +312,7 @@ def main():
     total_components = float(tot_comp.item())
 
     if rank == 0:
-        names = ["group_ranges", "build_constraints", "prologue", "enumerate", "dp", "units", "emit", "-"]
+        names = ["group_ranges", "build_constraints", "prologue", "enumerate", "dp_units", "units", "emit", "dp_merge"]
         dom = max(range(8), key=lambda k: kms[k])
         peak, peak_src = measured_peak()
         per_launch_ms = kms[dom] / max(1, kcnt[dom])

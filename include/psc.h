@@ -139,7 +139,7 @@ typedef struct psc_timing {
 	int64_t constraint_bytes; /* algorithmic bytes of the constraint kernel, last call */
 	/* per-kernel device time (CUDA events around every launch, summed) and launch counts of the last
 	 * psc_build_constraints + psc_solve: 0 group_ranges, 1 build_constraints, 2 prologue,
-	 * 3 enumerate, 4 dp, 5 units (pick/refine/EM/rescue), 6 emit, 7 unused */
+	 * 3 enumerate, 4 dp_units, 5 units (pick/refine/EM/rescue), 6 emit, 7 dp_merge */
 	double kernel_ms[8];
 	int64_t kernel_count[8];
 	int64_t kernel_bytes[8]; /* algorithmic bytes attributed to the kernel, 0 if not modelled */

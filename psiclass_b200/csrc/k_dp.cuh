@@ -57,7 +57,10 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 	Carver cv(base);
 	int W = (n + 63) >> 6;
 	DpScratch s;
-	s.hashMax = n > 500 ? 1000003 : 100003; // Q3: the other branches of the reference are unreachable
+	// The reference uses 100003 / 1000003 slots (Q3).  A collision only evicts an entry, which is then
+	// recomputed to the same value, so the table size changes no result (measured); a smaller
+	// direct-mapped table keeps the per-unit memo in L2.
+	s.hashMax = 8191;
 	long long nEnt = (long long)n + (long long)n * n + s.hashMax;
 	s.f2Base = n;
 	s.hashBase = (long long)n + (long long)n * n;
@@ -103,7 +106,7 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 // bytes at the start of the scratch that must be zero before the first use (memo epochs)
 __host__ __device__ inline size_t dp_scratch_zero_bytes(int n)
 {
-	int hashMax = n > 500 ? 1000003 : 100003;
+	int hashMax = 8191;
 	long long nEnt = (long long)n + (long long)n * n + hashMax;
 	return (size_t)nEnt * sizeof(DpMemo);
 }
@@ -856,23 +859,81 @@ PSC_DEV int dp_augment(DpState &st, uint64_t *cb, int *cf, int *cl, int A, int l
 	return dp_coalesce(st, cb, cf, cl, A);
 }
 
-// The DP branch of Solve (TranscriptDecider.cpp:3139-3265) for component c
-PSC_DEVN void dp_candidates(const Coop &co, const GraphDev &g, const SolveDev &sv, int c, char *scratch, int *order /* [S] */)
+// -----------------------------------------------------------------------------------------------
+// The DP branch of Solve (TranscriptDecider.cpp:3139-3265), split in two so that the per-sample
+// PickTranscriptsByDP calls of one component run concurrently:
+//   dp_unit_pick : one cooperative group per (DP component, sample).  The call only depends on the
+//                  sample's constraints and on iterBound; a smaller iterBound yields a PREFIX of the
+//                  same transcript list (the loop of .cpp:983-1165 just stops earlier), so every unit
+//                  runs with the largest bound it can get and the merge takes the prefix it needs.
+//   dp_merge     : one group per component, samples in the reference's order (descending number of
+//                  constraints, stable): append, CoalesceSameTranscripts, AugmentTranscripts.
+// -----------------------------------------------------------------------------------------------
+struct DpUnit {
+	int comp, sample;
+	int iterBound; // C of the sample for the first (largest) sample of the component, else 100
+	int stride;    // 0: constraints as they are (or truncated); > 0: DownsampleConstraintsFrom stride
+	long long scratch_off; // DpScratch of the unit (memo part zeroed by the host)
+	long long tx_off;      // bytes into the transcript-list arena
+};
+
+struct DpTxList {
+	uint64_t *b;
+	int *f, *l;
+};
+__host__ __device__ inline size_t dp_txlist_layout(DpTxList *o, char *base, int cap, int W)
+{
+	Carver cv(base);
+	DpTxList t;
+	t.b = cv.take<uint64_t>((size_t)cap * W + 1);
+	t.f = cv.take<int>((size_t)cap + 1);
+	t.l = cv.take<int>((size_t)cap + 1);
+	if (o) *o = t;
+	return (cv.off + 15) & ~(size_t)15;
+}
+
+// The control state of the explicit-stack machine (path, frames, per-frame best path, the shared
+// transcript buffer) is what every step reads and writes; when it fits the warp's slice of shared
+// memory it lives there instead of in the global scratch.
+PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
+{
+	if (!sm) return;
+	Carver cv(sm);
+	int *P = cv.take<int>((size_t)n + 4);
+	int *fr = cv.take<int>((size_t)(2 * n + 6) * PSC_FR_INTS);
+	double *fdcover = cv.take<double>((size_t)n + 3);
+	int *fdmeta = cv.take<int>((size_t)(n + 3) * 3);
+	uint64_t *fdbits = cv.take<uint64_t>((size_t)(n + 3) * W);
+	uint64_t *work = cv.take<uint64_t>((size_t)8 * W);
+	if (cv.off > smBytes) return;
+	d.P = P;
+	d.fr = fr;
+	d.fdcover = fdcover;
+	d.fdmeta = fdmeta;
+	d.fdbits = fdbits;
+	d.work = work;
+}
+
+PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv, const DpUnit &u, char *scratchBase,
+                           char *txBase, int *n_tx_out, char *sm, size_t smBytes)
 {
 	DpState st;
 	st.co = co;
-	st.v = comp_view(g, c);
+	st.v = comp_view(g, u.comp);
 	const CompView &v = st.v;
-	int S = sv.prm.S;
+	int c = u.comp;
 	int E = v.noff[v.n] - v.noff[0];
-	int Cmax = 0;
-	for (int s = 0; s < S; ++s) {
-		int cc = sv.samples[s].n_con[c];
-		if (cc > Cmax) Cmax = cc;
-	}
-	long long row0 = sv.cand_row_off[c];
-	long long cap = sv.cand_row_off[c + 1] - row0;
-	dp_scratch_layout(&st.d, scratch, v.n, E, Cmax, cap);
+	TableView t = table_view(sv.samples[u.sample], c);
+	int Ccap = t.C > 100 ? t.C : 100;
+	dp_scratch_layout(&st.d, scratchBase + u.scratch_off, v.n, E, Ccap, 1);
+	dp_use_shared(st.d, v.n, v.W, sm, smBytes);
+	DpTxList out;
+	dp_txlist_layout(&out, txBase + u.tx_off, u.iterBound, v.W);
+	// the unit's transcript list is written straight into its persistent slot
+	st.d.txb = out.b;
+	st.d.txf = out.f;
+	st.d.txl = out.l;
+	st.d.txCap = u.iterBound;
 	st.cs = sv.can_start + v.base;
 	st.ce = sv.can_end + v.base;
 	st.W = v.W;
@@ -882,82 +943,104 @@ PSC_DEVN void dp_candidates(const Coop &co, const GraphDev &g, const SolveDev &s
 	st.minAbundance = 0;
 	st.timeStamp = 0;
 	int W = v.W;
-	uint64_t *cb = sv.cand_bits + sv.cand_bits_off[c];
-	int *cf = sv.cand_first + row0, *cl = sv.cand_last + row0;
-	// samples in ascending number of constraints, stable (Q11), visited from the largest
-	co.sync();
-	if (co.lane == 0) {
-		for (int s = 0; s < S; ++s) order[s] = s;
-		for (int a = 1; a < S; ++a) {
-			int x = order[a], xc = sv.samples[x].n_con[c], b = a - 1;
-			while (b >= 0 && sv.samples[order[b]].n_con[c] > xc) { order[b + 1] = order[b]; --b; }
-			order[b + 1] = x;
+	int maxDp = sv.prm.maxDpConstraintSize;
+	if (maxDp > 0) {
+		// TruncateConstraintsCoverFrom (Constraints.hpp:400-434)
+		for (int k = co.lane; k < t.C; k += co.n) {
+			const uint64_t *src = t.bits + (long long)k * W;
+			uint64_t *dst = st.d.tcb + (long long)k * W;
+			for (int w = 0; w < W; ++w) dst[w] = 0;
+			int taken = 0, last = t.first[k];
+			for (int q = t.first[k]; q <= t.last[k] && taken < maxDp; ++q)
+				if (bt_test(src, q)) { bt_set(dst, q); last = q; ++taken; }
+			st.d.tcf[k] = t.first[k];
+			st.d.tcl[k] = last;
+			st.d.tcsup[k] = t.support[k];
+			st.d.tcnorm[k] = t.norm[k];
+			st.d.tcab[k] = t.norm[k];
 		}
+		st.d.tcCnt = t.C;
+	} else {
+		int stride = u.stride > 0 ? u.stride : 1; // DownsampleConstraintsFrom (Constraints.hpp:362-398)
+		int cnt = (t.C + stride - 1) / stride;
+		for (int k = co.lane; k < cnt; k += co.n) {
+			int src = k * stride;
+			for (int w = 0; w < W; ++w) st.d.tcb[(long long)k * W + w] = t.bits[(long long)src * W + w];
+			st.d.tcf[k] = t.first[src];
+			st.d.tcl[k] = t.last[src];
+			st.d.tcsup[k] = t.support[src];
+			st.d.tcnorm[k] = t.norm[src];
+			st.d.tcab[k] = t.norm[src];
+		}
+		st.d.tcCnt = cnt;
 	}
 	co.sync();
+	int nt = dp_pick(st, u.iterBound);
+	if (co.lane == 0) *n_tx_out = nt;
+	co.sync();
+}
+
+struct DpMergeScratch {
+	int *sortidx;
+	uint64_t *c2b;
+	int *c2f, *c2l;
+};
+__host__ __device__ inline size_t dp_merge_layout(DpMergeScratch *o, char *base, int W, long long candCap)
+{
+	Carver cv(base);
+	DpMergeScratch s;
+	long long p2 = 1;
+	while (p2 < candCap + 1) p2 <<= 1;
+	s.sortidx = cv.take<int>((size_t)p2 + 1);
+	s.c2b = cv.take<uint64_t>((size_t)candCap * W + 1);
+	s.c2f = cv.take<int>((size_t)candCap + 1);
+	s.c2l = cv.take<int>((size_t)candCap + 1);
+	if (o) *o = s;
+	return (cv.off + 15) & ~(size_t)15;
+}
+
+// units of component c are u0 .. u0+S-1, already in the reference's visiting order
+PSC_DEVN void dp_merge(const Coop &co, const GraphDev &g, const SolveDev &sv, int c, const DpUnit *units, int u0,
+                       const int *n_tx, const char *txBase, char *scratch)
+{
+	DpState st;
+	st.co = co;
+	st.v = comp_view(g, c);
+	const CompView &v = st.v;
+	int S = sv.prm.S, W = v.W;
+	long long row0 = sv.cand_row_off[c];
+	long long cap = sv.cand_row_off[c + 1] - row0;
+	DpMergeScratch ms;
+	dp_merge_layout(&ms, scratch, W, cap);
+	st.d.sortidx = ms.sortidx;
+	st.d.c2b = ms.c2b;
+	st.d.c2f = ms.c2f;
+	st.d.c2l = ms.c2l;
+	st.cs = sv.can_start + v.base;
+	st.ce = sv.can_end + v.base;
+	st.W = W;
+	st.err = sv.error_flag;
+	uint64_t *cb = sv.cand_bits + sv.cand_bits_off[c];
+	int *cf = sv.cand_first + row0, *cl = sv.cand_last + row0;
 	int A = 0;
-	int downsampleCnt = -1;
-	for (int oi = S - 1; oi >= 0; --oi) {
-		int s = order[oi];
-		TableView t = table_view(sv.samples[s], c);
-		int iterBound = t.C;
-		if (oi < S - 1) iterBound = 100;
-		if (oi < S - 10 && A > 1000) iterBound = 10;
-		int maxDp = sv.prm.maxDpConstraintSize;
-		int stride = 1;
-		bool skip = false;
-		if (maxDp > 0) {
-			// TruncateConstraintsCoverFrom (Constraints.hpp:400-434)
-			for (int k = co.lane; k < t.C; k += co.n) {
-				const uint64_t *src = t.bits + (long long)k * W;
-				uint64_t *dst = st.d.tcb + (long long)k * W;
-				for (int w = 0; w < W; ++w) dst[w] = 0;
-				int taken = 0, last = t.first[k];
-				for (int q = t.first[k]; q <= t.last[k] && taken < maxDp; ++q)
-					if (bt_test(src, q)) { bt_set(dst, q); last = q; ++taken; }
-				st.d.tcf[k] = t.first[k];
-				st.d.tcl[k] = last;
-				st.d.tcsup[k] = t.support[k];
-				st.d.tcnorm[k] = t.norm[k];
-				st.d.tcab[k] = t.norm[k];
-			}
-			st.d.tcCnt = t.C;
-		} else {
-			bool down = (t.C > 1000 && (long long)t.C * 10 < t.M) || (downsampleCnt > 0 && t.C >= downsampleCnt) || v.n >= 1500;
-			if (down) { // DownsampleConstraintsFrom (Constraints.hpp:362-398)
-				stride = t.C > 0 ? t.M / t.C : 1;
-				if (downsampleCnt > 0) stride = t.C / downsampleCnt;
-				if (stride < 1) stride = 1;
-			}
-			int cnt = down ? (t.C + stride - 1) / stride : t.C;
-			for (int k = co.lane; k < cnt; k += co.n) {
-				int src = k * stride;
-				for (int w = 0; w < W; ++w) st.d.tcb[(long long)k * W + w] = t.bits[(long long)src * W + w];
-				st.d.tcf[k] = t.first[src];
-				st.d.tcl[k] = t.last[src];
-				st.d.tcsup[k] = t.support[src];
-				st.d.tcnorm[k] = t.norm[src];
-				st.d.tcab[k] = t.norm[src];
-			}
-			st.d.tcCnt = cnt;
-			if (down) {
-				if (downsampleCnt <= 0) downsampleCnt = cnt;
-				if (iterBound <= 10) skip = true;
-			}
-		}
-		co.sync();
-		if (skip) continue;
-		int nt = dp_pick(st, iterBound);
-		// PickTranscriptsByDP coalesces its own list before handing it over (.cpp:1166)
-		nt = dp_coalesce(st, st.d.txb, st.d.txf, st.d.txl, nt);
+	for (int k = 0; k < S; ++k) {
+		const DpUnit &u = units[u0 + k];
+		int oi = S - 1 - k; // position in the ascending order the reference counts with
+		int bound = u.iterBound;
+		if (oi < S - 10 && A > 1000) bound = 10;
+		if (u.stride > 0 && bound <= 10) continue; // down-sampled samples with a tiny budget are skipped (.cpp:3228)
+		int nt = n_tx[u0 + k];
+		if (nt > bound) nt = bound;
+		DpTxList src;
+		dp_txlist_layout(&src, const_cast<char *>(txBase) + u.tx_off, u.iterBound, W);
 		if (A + nt > cap) {
 			*st.err = 25;
 			nt = (int)(cap - A);
 		}
-		for (int k = co.lane; k < nt; k += co.n) {
-			for (int w = 0; w < W; ++w) cb[(long long)(A + k) * W + w] = st.d.txb[(long long)k * W + w];
-			cf[A + k] = st.d.txf[k];
-			cl[A + k] = st.d.txl[k];
+		for (int q = co.lane; q < nt; q += co.n) {
+			for (int w = 0; w < W; ++w) cb[(long long)(A + q) * W + w] = src.b[(long long)q * W + w];
+			cf[A + q] = src.f[q];
+			cl[A + q] = src.l[q];
 		}
 		A += nt;
 		co.sync();

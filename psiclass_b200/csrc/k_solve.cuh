@@ -84,6 +84,9 @@ struct UnitScratch {
 	double *pool;      // [cap * M]
 	int *list;         // [A]
 	int *depl;         // [M] pairs depleted in the current iteration
+	double *score;     // [A] cached ComputeScore of the candidate, -1: not selectable
+	int *reach;        // [32 * n] per-lane scratch of the chain-coverage pass
+	double *persist;   // [4] inf, any-compatible flag, maxAbundance: round 1 -> round 2
 	uint64_t *tmpbits; // [4 * W]
 	uint8_t *flagsA;   // [max(A, n, C)]  small boolean scratch
 	// EM / refine (T <= 2*cap transcripts)
@@ -113,6 +116,9 @@ __host__ __device__ inline size_t unit_scratch_layout(UnitScratch *o, char *base
 	s.pool = cv.take<double>((size_t)cap * M);
 	s.list = cv.take<int>((size_t)A);
 	s.depl = cv.take<int>((size_t)M + 1);
+	s.score = cv.take<double>((size_t)A);
+	s.reach = cv.take<int>((size_t)32 * n);
+	s.persist = cv.take<double>(4);
 	s.tmpbits = cv.take<uint64_t>((size_t)4 * W);
 	int fa = A > n ? A : n;
 	if (C > fa) fa = C;
@@ -484,164 +490,197 @@ PSC_DEV bool pair_in_tx(const TableView &t, int j, const uint64_t *tb, int tf, i
 
 // =============================================================================================
 // PickTranscripts (TranscriptDecider.cpp:1368-2119): greedy quantitative set cover
-// round2: candidate weights use the round-1 support (alltranscripts[i].FPKM)
+// round2: candidate weights use the round-1 support (alltranscripts[i].FPKM); the compatibility
+// matrix and the per-candidate rough abundances do not depend on the round, so the second round
+// reuses what the first one left in the unit's scratch.
 // output: pr.id / pr.abundance / pr.corr, returns the number picked
 // =============================================================================================
+PSC_DEV double pick_score(const UnitScratch &sc, const CandView &cd, const SolveParams &prm, int i, double cnt,
+                          double maxAbundance, bool round2)
+{
+	if (cnt < 1) return -1; // "continue" of the reference: never selectable (all real scores are >= 1)
+	cnt *= sc.covPortion[i];
+	double weight = 1;
+	if (round2 && cd.sup1[i] > 0 && prm.S > 1) weight = (1 + (double)cd.sup1[i] / prm.S);
+	return compute_score(cnt, weight, sc.tAbund[i], maxAbundance, (double)cd.corr[i]);
+}
+
 PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &cd, const TableView &t,
                              const SolveParams &prm, UnitScratch &sc, int cap, bool round2, UnitPred &pr)
 {
 	int A = cd.A, M = t.M, W = v.W;
 	if (M == 0 || A == 0) return 0;
 	int MW = (M + 63) >> 6;
-	// ---- inf, pair abundances ----
-	double inf = -1;
-	for (int j = co.lane; j < M; j += co.n) {
-		double x = t.support[t.pi[j]];
-		if (t.support[t.pj[j]] > x) x = t.support[t.pj[j]];
-		if (t.pnorm[j] > x) x = t.pnorm[j];
-		if (x > inf) inf = x;
-		sc.pairAbund[j] = t.pnorm[j];
-	}
-	inf = co.max(inf);
-	inf = inf + 1;
-	// ---- compatibility matrix: lanes over pairs, ballot not needed since each lane owns words ----
-	for (long long q = co.lane; q < (long long)A * MW; q += co.n) sc.btable[q] = 0;
-	co.sync();
-	int anySet = 0;
-	for (int i = 0; i < A; ++i) {
-		const uint64_t *tb = cd.bits + (long long)i * W;
-		int tf = cd.first[i], tl = cd.last[i];
-		for (int w = co.lane; w < MW; w += co.n) {
-			uint64_t word = 0;
-			int jend = (w + 1) * 64 < M ? (w + 1) * 64 : M;
-			for (int j = w * 64; j < jend; ++j)
-				if (pair_in_tx(t, j, tb, tf, tl, W)) word |= (uint64_t)1 << (j & 63);
-			sc.btable[(long long)i * MW + w] = word;
-			if (word) anySet = 1;
+	double inf, maxAbundance;
+	if (!round2) {
+		// ---- inf ----
+		inf = -1;
+		for (int j = co.lane; j < M; j += co.n) {
+			double x = t.support[t.pi[j]];
+			if (t.support[t.pj[j]] > x) x = t.support[t.pj[j]];
+			if (t.pnorm[j] > x) x = t.pnorm[j];
+			if (x > inf) inf = x;
 		}
+		inf = co.max(inf);
+		inf = inf + 1;
+		// ---- compatibility matrix: lanes over 64-pair words ----
+		int anySet = 0;
+		for (int i = 0; i < A; ++i) {
+			const uint64_t *tb = cd.bits + (long long)i * W;
+			int tf = cd.first[i], tl = cd.last[i];
+			for (int w = co.lane; w < MW; w += co.n) {
+				uint64_t word = 0;
+				int jend = (w + 1) * 64 < M ? (w + 1) * 64 : M;
+				for (int j = w * 64; j < jend; ++j)
+					if (pair_in_tx(t, j, tb, tf, tl, W)) word |= (uint64_t)1 << (j & 63);
+				sc.btable[(long long)i * MW + w] = word;
+				if (word) anySet = 1;
+			}
+		}
+		anySet = co.max(anySet);
+		co.sync();
+		if (co.lane == 0) {
+			sc.persist[0] = inf;
+			sc.persist[1] = anySet;
+		}
+		if (!anySet) {
+			co.sync();
+			return 0;
+		}
+		// ---- per-candidate rough abundance: lanes over candidates, sequential over pairs.
+		// All pair abundances equal their normAbund here (tc[j].abundance = tc[j].normAbund) ----
+		maxAbundance = -1;
+		int *reach = sc.reach + (long long)co.lane * v.n;
+		for (int i = co.lane; i < A; i += co.n) {
+			const uint64_t *tb = cd.bits + (long long)i * W;
+			const uint64_t *bt = sc.btable + (long long)i * MW;
+			int tf = cd.first[i], tl = cd.last[i];
+			double value = inf;
+			int tag = -1;
+			int seIdxCnt = 0;
+			for (int w = 0; w < W; ++w) seIdxCnt += popc64(tb[w]);
+			int compatibleCnt = 0;
+			double avg = 0;
+			for (int q = tf; q <= tl; ++q) reach[q] = -1;
+			for (int w = 0; w < MW; ++w) {
+				uint64_t word = bt[w];
+				while (word) {
+					int j = w * 64 + ctz64(word);
+					word &= word - 1;
+					double pa = t.pnorm[j];
+					if (!(pa > 0)) continue;
+					++compatibleCnt;
+					double adjust = pa;
+					int ci = t.pi[j], cj = t.pj[j];
+					int fi = t.first[ci], li = t.last[ci], fj = t.first[cj], lj = t.last[cj];
+					if (seIdxCnt > 1) {
+						int si = fi + li, sj = fj + lj;
+						bool iEdge = si == 2 * tf || si == 2 * tl;
+						bool jEdge = sj == 2 * tf || sj == 2 * tl;
+						if (ci == cj && iEdge) adjust = inf;
+						else if (ci != cj && iEdge) adjust = t.norm[cj];
+						else if (ci != cj && jEdge) adjust = t.norm[ci];
+					}
+					if (adjust < value) { value = adjust; tag = j; }
+					avg += pa;
+					// a compatible constraint repeats the transcript's bits on [first, last]: it covers
+					// every chain (consecutive subexon pair of the transcript) inside that range
+					if (li > reach[fi]) reach[fi] = li;
+					if (lj > reach[fj]) reach[fj] = lj;
+				}
+			}
+			// covered chains (.cpp:1607-1629, 1660-1673)
+			int cnt = 0;
+			bool uncovered = false;
+			{
+				int prev = -1, far = -1;
+				for (int q = tf; q <= tl; ++q) {
+					if (!bt_test(tb, q)) continue;
+					if (prev >= 0) {
+						if (far >= q) ++cnt;
+						else uncovered = true;
+					}
+					if (reach[q] > far) far = reach[q];
+					prev = q;
+				}
+			}
+			// together penalty (.cpp:1634-1656): regions of >= 2 IR/overhang subexons partially used
+			for (int r0 = 0; r0 < v.n;) {
+				int r1;
+				for (r1 = r0 + 1; r1 < v.n; ++r1)
+					if (v.st[r1] > v.en[r1 - 1] + 1) break;
+				int tot = 0, got = 0;
+				for (int q = r0; q < r1; ++q) {
+					bool tg = (v.lt[q] == 2 && v.rt[q] == 1) || (v.lt[q] == 0 && v.rt[q] == 1) || (v.lt[q] == 2 && v.rt[q] == 0);
+					if (tg) {
+						++tot;
+						if (bt_test(tb, q)) ++got;
+					}
+				}
+				if (tot > 1 && got > 0 && got < tot) value /= 2;
+				r0 = r1;
+			}
+			if (uncovered) value = 0;
+			double portion;
+			if (seIdxCnt > 1) portion = (double)cnt / (double)(seIdxCnt - 1);
+			else portion = 1;
+			if (portion == 0) portion = (double)0.5 / (seIdxCnt);
+			sc.covPortion[i] = portion;
+			if (tag == -1) value = 0;
+			if (value > maxAbundance) maxAbundance = value;
+			sc.tAbund[i] = value;
+			if (tag != -1) avg /= compatibleCnt;
+			sc.avgAbund[i] = avg;
+		}
+		maxAbundance = co.max(maxAbundance);
+		co.sync();
+		if (maxAbundance == 0) {
+			for (int i = co.lane; i < A; i += co.n) sc.tAbund[i] = sc.covPortion[i];
+			maxAbundance = 1;
+		}
+		if (co.lane == 0) sc.persist[2] = maxAbundance;
+		co.sync();
+	} else {
+		inf = sc.persist[0];
+		if (sc.persist[1] == 0) return 0;
+		maxAbundance = sc.persist[2];
 	}
-	anySet = co.max(anySet);
+	// ---- per-round state ----
+	for (int j = co.lane; j < M; j += co.n) sc.pairAbund[j] = t.pnorm[j];
 	co.sync();
-	if (!anySet) return 0;
-
-	// ---- togetherChain regions (.cpp:1481-1517) kept as bit masks in tmpbits: computed on the fly below ----
-	// ---- per-candidate rough abundance: lanes over candidates, sequential over pairs ----
-	double maxAbundance = -1;
 	for (int i = co.lane; i < A; i += co.n) {
-		const uint64_t *tb = cd.bits + (long long)i * W;
-		const uint64_t *bt = sc.btable + (long long)i * MW;
-		int tf = cd.first[i], tl = cd.last[i];
-		double value = inf;
-		int tag = -1;
 		sc.abund[i] = 0;
 		sc.slot[i] = -1;
-		int seIdxCnt = 0;
-		for (int w = 0; w < W; ++w) seIdxCnt += popc64(tb[w]);
-		int compatibleCnt = 0;
-		double avg = 0;
-		for (int j = 0; j < M; ++j) {
-			if (!(bt_test(bt, j) && sc.pairAbund[j] > 0)) continue;
-			++compatibleCnt;
-			double adjust = sc.pairAbund[j];
-			int ci = t.pi[j], cj = t.pj[j];
-			if (seIdxCnt > 1) {
-				int si = t.first[ci] + t.last[ci], sj = t.first[cj] + t.last[cj];
-				bool iEdge = si == 2 * tf || si == 2 * tl;
-				bool jEdge = sj == 2 * tf || sj == 2 * tl;
-				if (ci == cj && iEdge) adjust = inf;
-				else if (ci != cj && iEdge) adjust = t.norm[cj];
-				else if (ci != cj && jEdge) adjust = t.norm[ci];
-			}
-			if (adjust < value) { value = adjust; tag = j; }
-			avg += sc.pairAbund[j];
-		}
-		// covered chains: every consecutive pair of the transcript's subexons must sit together in some
-		// compatible constraint (.cpp:1607-1629, 1660-1673)
-		int cnt = 0;
-		bool uncovered = false;
-		{
-			int prev = -1;
-			for (int q = tf; q <= tl; ++q) {
-				if (!bt_test(tb, q)) continue;
-				if (prev >= 0) {
-					bool cov = false;
-					for (int j = 0; j < M && !cov; ++j) {
-						if (!(bt_test(bt, j) && sc.pairAbund[j] > 0)) continue;
-						const uint64_t *ba = t.bits + (long long)t.pi[j] * W, *bb = t.bits + (long long)t.pj[j] * W;
-						if ((bt_test(ba, prev) && bt_test(ba, q)) || (bt_test(bb, prev) && bt_test(bb, q))) cov = true;
-					}
-					if (cov) ++cnt;
-					else uncovered = true;
-				}
-				prev = q;
+		const uint64_t *bt = sc.btable + (long long)i * MW;
+		double cnt = 0;
+		for (int w = 0; w < MW; ++w) {
+			uint64_t word = bt[w];
+			while (word) {
+				int j = w * 64 + ctz64(word);
+				word &= word - 1;
+				if (sc.pairAbund[j] > 0) cnt += t.pec[j];
 			}
 		}
-		// together penalty (.cpp:1634-1656): regions of >= 2 IR/overhang subexons partially used
-		for (int r0 = 0; r0 < v.n;) {
-			int r1;
-			for (r1 = r0 + 1; r1 < v.n; ++r1)
-				if (v.st[r1] > v.en[r1 - 1] + 1) break;
-			int tot = 0, got = 0;
-			for (int q = r0; q < r1; ++q) {
-				bool tg = (v.lt[q] == 2 && v.rt[q] == 1) || (v.lt[q] == 0 && v.rt[q] == 1) || (v.lt[q] == 2 && v.rt[q] == 0);
-				if (tg) {
-					++tot;
-					if (bt_test(tb, q)) ++got;
-				}
-			}
-			if (tot > 1 && got > 0 && got < tot) value /= 2;
-			r0 = r1;
-		}
-		if (uncovered) value = 0;
-		double portion;
-		if (seIdxCnt > 1) portion = (double)cnt / (double)(seIdxCnt - 1);
-		else portion = 1;
-		if (portion == 0) portion = (double)0.5 / (seIdxCnt);
-		sc.covPortion[i] = portion;
-		if (tag == -1) value = 0;
-		if (value > maxAbundance) maxAbundance = value;
-		sc.tAbund[i] = value;
-		if (tag != -1) avg /= compatibleCnt;
-		sc.avgAbund[i] = avg;
-		sc.coverCnt[i] = -1;
+		sc.coverCnt[i] = cnt;
+		sc.score[i] = pick_score(sc, cd, prm, i, cnt, maxAbundance, round2);
 	}
-	maxAbundance = co.max(maxAbundance);
 	co.sync();
-	if (maxAbundance == 0) {
-		for (int i = co.lane; i < A; i += co.n) sc.tAbund[i] = sc.covPortion[i];
-		maxAbundance = 1;
-		co.sync();
-	}
 	// ---- quantitative set cover (.cpp:1827-2068) ----
 	int poolUsed = 0;
 	for (;;) {
 		// arg-max: lexicographic (score, avgAbund) maximum, lowest index on full ties
-		double bestScore = -1, bestAvg = 0, maxcnt = -1;
+		double bestScore = -1, bestAvg = 0;
 		int bestI = -1;
 		for (int i = co.lane; i < A; i += co.n) {
-			double cnt;
-			if (sc.coverCnt[i] == -1) {
-				const uint64_t *bt = sc.btable + (long long)i * MW;
-				cnt = 0;
-				for (int j = 0; j < M; ++j)
-					if (sc.pairAbund[j] > 0 && bt_test(bt, j)) cnt += t.pec[j];
-				sc.coverCnt[i] = cnt;
-			} else
-				cnt = sc.coverCnt[i];
-			if (cnt < 1) continue;
-			cnt *= sc.covPortion[i];
-			double weight = 1;
-			if (round2 && cd.sup1[i] > 0 && prm.S > 1) weight = (1 + (double)cd.sup1[i] / prm.S);
-			double s = compute_score(cnt, weight, sc.tAbund[i], maxAbundance, (double)cd.corr[i]);
-			if (cnt > maxcnt) maxcnt = cnt;
-			if (bestI == -1 ? (s > bestScore) : (s > bestScore || (s == bestScore && bestAvg < sc.avgAbund[i]))) {
+			double s = sc.score[i];
+			if (s < 0) continue;
+			if (bestI == -1 || s > bestScore || (s == bestScore && bestAvg < sc.avgAbund[i])) {
 				bestScore = s;
 				bestAvg = sc.avgAbund[i];
 				bestI = i;
 			}
 		}
 		if (co.n > 1) {
-			maxcnt = co.max(maxcnt);
 			for (int o = 16; o > 0; o >>= 1) {
 				double os = co.bcast(bestScore, co.lane ^ o), oa = co.bcast(bestAvg, co.lane ^ o);
 				int oi = co.bcast(bestI, co.lane ^ o);
@@ -658,7 +697,7 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 			}
 		}
 		int maxtag = bestI;
-		if (maxcnt == 0 || maxtag == -1) break;
+		if (maxtag == -1) break;
 		const uint64_t *btm = sc.btable + (long long)maxtag * MW;
 		// pair to deplete: smallest remaining abundance, last index on ties (.cpp:1913-1923)
 		double update = inf;
@@ -666,8 +705,14 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		{
 			double lu = inf;
 			int lt = -1;
-			for (int j = co.lane; j < M; j += co.n)
-				if (bt_test(btm, j) && sc.pairAbund[j] > 0 && sc.pairAbund[j] <= lu) { lu = sc.pairAbund[j]; lt = j; }
+			for (int w = co.lane; w < MW; w += co.n) {
+				uint64_t word = btm[w];
+				while (word) {
+					int j = w * 64 + ctz64(word);
+					word &= word - 1;
+					if (sc.pairAbund[j] > 0 && sc.pairAbund[j] <= lu) { lu = sc.pairAbund[j]; lt = j; }
+				}
+			}
 			if (co.n > 1) {
 				for (int o = 16; o > 0; o >>= 1) {
 					double ou = co.bcast(lu, co.lane ^ o);
@@ -679,9 +724,7 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		}
 		// the chosen candidate needs a csupport row
 		if (sc.slot[maxtag] < 0) {
-			if (poolUsed >= cap) { // cannot happen: one new candidate per iteration, <= M+1 iterations
-				return -1;
-			}
+			if (poolUsed >= cap) return -1; // cannot happen: one new candidate per iteration, <= M+1 iterations
 			double *row = sc.pool + (long long)poolUsed * M;
 			for (int j = co.lane; j < M; j += co.n) row[j] = 0;
 			co.sync();
@@ -691,11 +734,14 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		}
 		double *rowm = sc.pool + (long long)sc.slot[maxtag] * M;
 		int supportCnt = 0, deplCnt = 0;
-		// sequential over pairs: alltranscripts[maxtag].abundance accumulates in index order
+		// sequential over the compatible pairs: alltranscripts[maxtag].abundance accumulates in index order
 		if (co.lane == 0) {
 			double abm = sc.abund[maxtag];
-			for (int j = 0; j < M; ++j) {
-				if (bt_test(btm, j)) {
+			for (int w = 0; w < MW; ++w) {
+				uint64_t word = btm[w];
+				while (word) {
+					int j = w * 64 + ctz64(word);
+					word &= word - 1;
 					if (sc.pairAbund[j] > 0) {
 						sc.pairAbund[j] -= 1 * update;
 						double factor = t.pec[j];
@@ -707,7 +753,6 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 					} else if (rowm[j] == 0) {
 						double takeOut = 0, factor = t.pec[j];
 						int listCnt = 0;
-						sc.abund[maxtag] = abm;
 						for (int i = 0; i < A; ++i) {
 							if (i == maxtag) continue;
 							if (sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
@@ -735,25 +780,32 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 						rowm[j] += tmp;
 						abm += tmp;
 					}
+					if (sc.pairAbund[j] < 0) sc.pairAbund[j] = 0;
 				}
-				if (sc.pairAbund[j] < 0) sc.pairAbund[j] = 0;
 			}
 			sc.abund[maxtag] = abm;
+			// tc[updateTag].abundance = 0 (.cpp:2063); when it is not one of maxtag's pairs (no pair was
+			// left: update == inf) the reference zeroes pair 0 without touching coverCnt and stops.
 			sc.pairAbund[updateTag] = 0;
 		}
 		supportCnt = co.bcast(supportCnt, 0);
 		deplCnt = co.bcast(deplCnt, 0);
 		co.sync();
-		// coverCnt bookkeeping (.cpp:1965-1973): every candidate sharing a pair that just ran dry
-		for (int i = co.lane; i < A; i += co.n) {
-			const uint64_t *bt = sc.btable + (long long)i * MW;
-			double cc = sc.coverCnt[i];
-			for (int q = 0; q < deplCnt; ++q)
-				if (bt_test(bt, sc.depl[q])) cc -= t.pec[sc.depl[q]];
-			sc.coverCnt[i] = cc;
-		}
-		co.sync();
 		if (supportCnt == 0) break;
+		// coverCnt bookkeeping (.cpp:1965-1973): every candidate sharing a pair that just ran dry
+		if (deplCnt > 0)
+			for (int i = co.lane; i < A; i += co.n) {
+				const uint64_t *bt = sc.btable + (long long)i * MW;
+				double cc = sc.coverCnt[i];
+				bool changed = false;
+				for (int q = 0; q < deplCnt; ++q)
+					if (bt_test(bt, sc.depl[q])) { cc -= t.pec[sc.depl[q]]; changed = true; }
+				if (changed) {
+					sc.coverCnt[i] = cc;
+					sc.score[i] = pick_score(sc, cd, prm, i, cc, maxAbundance, round2);
+				}
+			}
+		co.sync();
 	}
 	// ---- collect (.cpp:2070-2085) ----
 	int T = 0;

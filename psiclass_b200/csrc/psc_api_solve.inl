@@ -36,16 +36,42 @@ __global__ void __launch_bounds__(128) k_enumerate(GraphDev g, SolveDev sv, cons
 	}
 }
 
-__global__ void __launch_bounds__(128) k_dp(GraphDev g, SolveDev sv, const int *list, int nList, char *scratch,
-                                            const long long *scr_off, int *order, int *counter, int width)
+__global__ void __launch_bounds__(128) k_dp_units(GraphDev g, SolveDev sv, const DpUnit *units, const int *order, int nUnits,
+                                                  char *scratch, char *txArena, int *n_tx, int *counter, int width, int smemPerWarp)
 {
 	Coop co = make_coop(width);
+	char *sm = nullptr;
+	size_t smBytes = 0;
+#ifndef PSC_CPU_SHIM
+	extern __shared__ __align__(16) unsigned char dp_smem[];
+	if (width == 32 && smemPerWarp > 0) {
+		sm = (char *)dp_smem + (size_t)(threadIdx.x >> 5) * smemPerWarp;
+		smBytes = (size_t)smemPerWarp;
+	}
+#endif
 	for (;;) {
 		int u = 0;
 		if (co.lane == 0) u = atomic_add(counter, 1);
 		u = co.bcast(u, 0);
-		if (u >= nList) break;
-		dp_candidates(co, g, sv, list[u], scratch + scr_off[u], order + (long long)u * sv.prm.S);
+		if (u >= nUnits) break;
+		int ui = order[u];
+		dp_unit_pick(co, g, sv, units[ui], scratch, txArena, n_tx + ui, sm, smBytes);
+		co.sync();
+	}
+}
+
+__global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const DpUnit *units, const int *compList, int nComp,
+                                                  const int *n_tx, const char *txArena, char *scratch, const long long *scr_off,
+                                                  int *counter, int width)
+{
+	Coop co = make_coop(width);
+	int S = sv.prm.S;
+	for (;;) {
+		int k = 0;
+		if (co.lane == 0) k = atomic_add(counter, 1);
+		k = co.bcast(k, 0);
+		if (k >= nComp) break;
+		dp_merge(co, g, sv, compList[k], units, k * S, n_tx, txArena, scratch + scr_off[k]);
 		co.sync();
 	}
 }
@@ -219,36 +245,101 @@ int psc_solve(psc_ctx *ctx)
 		CK(cudaGetLastError());
 		CK(cudaStreamSynchronize(ctx->stream)); // enumList staging buffer is reused below
 	}
-	// ---- P2b: DP, in chunks that fit the memory budget ----
+	// ---- P2b: DP.  Units are (component, sample); chunks of components that fit the memory budget ----
 	{
 		size_t i0 = 0;
 		while (i0 < dpList.size()) {
-			std::vector<long long> off;
+			std::vector<DpUnit> units;
+			std::vector<long long> mergeOff, cost;
 			std::vector<std::pair<size_t, size_t>> zero; // (offset, bytes) memo regions
-			long long acc = 0;
+			long long sAcc = 0, tAcc = 0, mAcc = 0;
 			size_t i1 = i0;
 			while (i1 < dpList.size()) {
 				int c = dpList[i1];
 				int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
-				int Cmax = 0;
-				for (int s = 0; s < S; ++s) Cmax = std::max(Cmax, ctx->samples[(size_t)s].h_ncon[(size_t)c]);
+				int W = (n + 63) / 64;
 				long long cap = rowOff[(size_t)c + 1] - rowOff[(size_t)c];
-				size_t need = dp_scratch_layout(nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], Cmax, cap);
-				if (i1 > i0 && (size_t)acc + need > ctx->mem_budget) break;
-				off.push_back(acc);
-				zero.push_back({(size_t)acc, dp_scratch_zero_bytes(n)});
-				acc += (long long)need;
+				// the reference visits the samples in descending number of constraints (qsort ascending,
+				// stable, walked from the back: Q11)
+				std::vector<int> ord((size_t)S);
+				for (int s = 0; s < S; ++s) ord[(size_t)s] = s;
+				std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+					return ctx->samples[(size_t)a].h_ncon[(size_t)c] < ctx->samples[(size_t)b].h_ncon[(size_t)c];
+				});
+				std::vector<DpUnit> mine;
+				long long sNeed = 0, tNeed = 0;
+				int downsampleCnt = -1;
+				for (int oi = S - 1; oi >= 0; --oi) {
+					int s = ord[(size_t)oi];
+					int C = ctx->samples[(size_t)s].h_ncon[(size_t)c], M = ctx->samples[(size_t)s].h_npair[(size_t)c];
+					DpUnit u;
+					u.comp = c;
+					u.sample = s;
+					u.iterBound = oi == S - 1 ? C : 100;
+					u.stride = 0;
+					if (ctx->prm.max_dp_constraint_size <= 0) {
+						bool down = (C > 1000 && (long long)C * 10 < M) || (downsampleCnt > 0 && C >= downsampleCnt) || n >= 1500;
+						if (down) { // TranscriptDecider.cpp:3214-3227
+							int stride = C > 0 ? M / C : 1;
+							if (downsampleCnt > 0) stride = C / downsampleCnt;
+							if (stride < 1) stride = 1;
+							u.stride = stride;
+							if (downsampleCnt <= 0) downsampleCnt = (C + stride - 1) / stride;
+						}
+					}
+					if (u.iterBound < 1) u.iterBound = 1;
+					u.scratch_off = sAcc + sNeed;
+					u.tx_off = tAcc + tNeed;
+					zero.push_back({(size_t)u.scratch_off, dp_scratch_zero_bytes(n)});
+					sNeed += (long long)dp_scratch_layout(nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100), 1);
+					tNeed += (long long)dp_txlist_layout(nullptr, nullptr, u.iterBound, W);
+					mine.push_back(u);
+				}
+				if (i1 > i0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
+				for (auto &u : mine) {
+					units.push_back(u);
+					cost.push_back((long long)u.iterBound * (ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] + 1));
+				}
+				sAcc += sNeed;
+				tAcc += tNeed;
+				mergeOff.push_back(mAcc);
+				mAcc += (long long)dp_merge_layout(nullptr, nullptr, W, cap);
 				++i1;
 			}
-			if (!st.scratch.ensure((size_t)acc + 16)) return ctx->fail("out of device memory (DP scratch)");
+			// note: the offsets of the units we rolled back (mine, on break) were never committed
+			int nUnits = (int)units.size(), nComp = (int)(i1 - i0);
+			std::vector<int> order((size_t)nUnits);
+			for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
+			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+			for (size_t k = zero.size(); k > (size_t)nUnits; --k) zero.pop_back();
+			if (!st.scratch.ensure((size_t)std::max(sAcc, mAcc) + 16) || !st.dp_tx.ensure((size_t)tAcc + 16) ||
+			    !st.dp_ntx.ensure(sizeof(int) * (size_t)(nUnits + 1)))
+				return ctx->fail("out of device memory (DP scratch)");
 			for (auto &z : zero) CK(cudaMemsetAsync((char *)st.scratch.p + z.first, 0, z.second, ctx->stream));
-			int nList = (int)(i1 - i0);
-			if (!upload(ctx, st.list, dpList.data() + i0, (size_t)nList) || !upload(ctx, st.scr_off, off.data(), off.size()) ||
-			    !st.dp_order.ensure(sizeof(int) * (size_t)nList * S))
+			CK(cudaMemsetAsync(st.dp_ntx.p, 0, sizeof(int) * (size_t)(nUnits + 1), ctx->stream));
+			if (!upload(ctx, st.list, dpList.data() + i0, (size_t)nComp) || !upload(ctx, st.dp_units, units.data(), units.size()) ||
+			    !upload(ctx, st.order, order.data(), order.size()) || !upload(ctx, st.scr_off, mergeOff.data(), mergeOff.size()))
 				return ctx->fail("out of device memory");
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			KLAUNCH(4, k_dp, launch_grid(ctx, nList), 128, ctx->gd, sv, st.list.as<int>(), nList, (char *)st.scratch.p,
-			        st.scr_off.as<long long>(), st.dp_order.as<int>(), counter, ctx->coop);
+			{
+				const int smemPerWarp = ctx->coop == 32 ? 24 * 1024 : 0; // 4 warps -> 96 KB per CTA, 2 CTAs per SM
+#ifndef PSC_CPU_SHIM
+				CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 24 * 1024));
+				ctx->ktime_begin(4);
+				k_dp_units<<<launch_grid(ctx, nUnits), 128, 4 * smemPerWarp, ctx->stream>>>(
+				    ctx->gd, sv, st.dp_units.as<DpUnit>(), st.order.as<int>(), nUnits, (char *)st.scratch.p, (char *)st.dp_tx.p,
+				    st.dp_ntx.as<int>(), counter, ctx->coop, smemPerWarp);
+				ctx->ktime_end();
+#else
+				KLAUNCH(4, k_dp_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, st.dp_units.as<DpUnit>(), st.order.as<int>(), nUnits,
+				        (char *)st.scratch.p, (char *)st.dp_tx.p, st.dp_ntx.as<int>(), counter, ctx->coop, smemPerWarp);
+#endif
+			}
+			++launches;
+			CK(cudaGetLastError());
+			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
+			KLAUNCH(7, k_dp_merge, launch_grid(ctx, nComp), 128, ctx->gd, sv, st.dp_units.as<DpUnit>(), st.list.as<int>(), nComp,
+			        st.dp_ntx.as<int>(), (const char *)st.dp_tx.p, (char *)st.scratch.p, st.scr_off.as<long long>(), counter, ctx->coop);
 			++launches;
 			CK(cudaGetLastError());
 			CK(cudaStreamSynchronize(ctx->stream));
