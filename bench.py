@@ -273,14 +273,14 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    dev_ms, kms, kcnt, kbytes, launches = 0.0, [0.0] * 8, [0] * 8, [0] * 8, 0
+    dev_ms, kms, kcnt, kbytes, launches = 0.0, [0.0] * 12, [0] * 12, [0] * 12, 0
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step_resident()
         tm = eng.timing()
         dev_ms += tm.constraints_ms + tm.solve_ms
         launches += tm.kernel_launches
-        for k in range(8):
+        for k in range(12):
             kms[k] += tm.kernel_ms[k]
             kcnt[k] += tm.kernel_count[k]
             kbytes[k] = tm.kernel_bytes[k]
@@ -312,8 +312,9 @@ def main():
     total_components = float(tot_comp.item())
 
     if rank == 0:
-        names = ["group_ranges", "build_constraints", "prologue", "enumerate", "dp_units", "units", "emit", "dp_merge"]
-        dom = max(range(8), key=lambda k: kms[k])
+        names = ["group_ranges", "build_constraints", "prologue", "enumerate", "dp_units", "units_pick1", "emit", "dp_merge",
+                 "units_pick2_refine_em", "units_rescue", "-", "-"]
+        dom = max(range(12), key=lambda k: kms[k])
         peak, peak_src = measured_peak()
         per_launch_ms = kms[dom] / max(1, kcnt[dom])
         # algorithmic bytes are modelled per step for kernels 1 and 5; per launch = per step / launches per step
@@ -332,7 +333,7 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "ms_per_launch": per_launch_ms},
-            "kernel_ms_per_step": {names[k]: kms[k] / a.steps for k in range(8) if kcnt[k]},
+            "kernel_ms_per_step": {names[k]: kms[k] / a.steps for k in range(12) if kcnt[k]},
             "device_ms_per_step": dev_ms / a.steps,
             "components_per_rank": ncomp, "transcripts_per_rank": int(ntx),
             "reads_per_rank": int(sum(r.n_reads for r in reads)),

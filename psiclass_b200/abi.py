@@ -63,7 +63,7 @@ class psc_comp_stats(C.Structure):
 
 class psc_timing(C.Structure):
     _fields_ = [("constraints_ms", C.c_double), ("solve_ms", C.c_double), ("kernel_launches", C.c_int64),
-                ("constraint_bytes", C.c_int64), ("kernel_ms", C.c_double * 8), ("kernel_count", C.c_int64 * 8), ("kernel_bytes", C.c_int64 * 8)]
+                ("constraint_bytes", C.c_int64), ("kernel_ms", C.c_double * 12), ("kernel_count", C.c_int64 * 12), ("kernel_bytes", C.c_int64 * 12)]
 
 
 # every symbol include/psc.h declares

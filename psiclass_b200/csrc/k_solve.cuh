@@ -85,6 +85,7 @@ struct UnitScratch {
 	int *list;         // [A]
 	int *depl;         // [M] pairs depleted in the current iteration
 	double *score;     // [A] cached ComputeScore of the candidate, -1: not selectable
+	double *contrib;   // [M] this iteration's support of maxtag per pair, -1: pair was already depleted
 	int *reach;        // [32 * n] per-lane scratch of the chain-coverage pass
 	double *persist;   // [4] inf, any-compatible flag, maxAbundance: round 1 -> round 2
 	uint64_t *tmpbits; // [4 * W]
@@ -117,6 +118,7 @@ __host__ __device__ inline size_t unit_scratch_layout(UnitScratch *o, char *base
 	s.list = cv.take<int>((size_t)A);
 	s.depl = cv.take<int>((size_t)M + 1);
 	s.score = cv.take<double>((size_t)A);
+	s.contrib = cv.take<double>((size_t)M + 1);
 	s.reach = cv.take<int>((size_t)32 * n);
 	s.persist = cv.take<double>(4);
 	s.tmpbits = cv.take<uint64_t>((size_t)4 * W);
@@ -734,7 +736,39 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		}
 		double *rowm = sc.pool + (long long)sc.slot[maxtag] * M;
 		int supportCnt = 0, deplCnt = 0;
-		// sequential over the compatible pairs: alltranscripts[maxtag].abundance accumulates in index order
+		int *dcount = sc.depl + M;
+		if (co.lane == 0) *dcount = 0;
+		co.sync();
+		// phase A, lanes over the words of maxtag's row: pairs that still have abundance (.cpp:1957-1975).
+		// Their contribution to alltranscripts[maxtag].abundance is parked in contrib[] and added in
+		// index order by phase B, so the fp64 sum keeps the reference's order.
+		{
+			int ls = 0;
+			for (int w = co.lane; w < MW; w += co.n) {
+				uint64_t word = btm[w];
+				while (word) {
+					int j = w * 64 + ctz64(word);
+					word &= word - 1;
+					double pa = sc.pairAbund[j];
+					if (pa > 0) {
+						pa -= 1 * update;
+						double factor = t.pec[j];
+						double tmp = (t.psup[j] * update / t.pnorm[j] * factor);
+						rowm[j] += tmp;
+						sc.contrib[j] = tmp;
+						if (pa <= 0) sc.depl[atomic_add(dcount, 1)] = j;
+						if (pa < 0) pa = 0;
+						sc.pairAbund[j] = pa;
+						++ls;
+					} else
+						sc.contrib[j] = -1; // depleted before this iteration: phase B looks at it
+				}
+			}
+			supportCnt = co.sum(ls);
+		}
+		co.sync();
+		// phase B, sequential in pair order: accumulate, and redistribute support for pairs that were
+		// already depleted and that this candidate never got a share of (.cpp:1976-2054)
 		if (co.lane == 0) {
 			double abm = sc.abund[maxtag];
 			for (int w = 0; w < MW; ++w) {
@@ -742,14 +776,9 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 				while (word) {
 					int j = w * 64 + ctz64(word);
 					word &= word - 1;
-					if (sc.pairAbund[j] > 0) {
-						sc.pairAbund[j] -= 1 * update;
-						double factor = t.pec[j];
-						double tmp = (t.psup[j] * update / t.pnorm[j] * factor);
-						rowm[j] += tmp;
-						abm += tmp;
-						if (sc.pairAbund[j] <= 0) sc.depl[deplCnt++] = j;
-						++supportCnt;
+					double cj = sc.contrib[j];
+					if (cj >= 0) {
+						abm += cj;
 					} else if (rowm[j] == 0) {
 						double takeOut = 0, factor = t.pec[j];
 						int listCnt = 0;
@@ -780,7 +809,6 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 						rowm[j] += tmp;
 						abm += tmp;
 					}
-					if (sc.pairAbund[j] < 0) sc.pairAbund[j] = 0;
 				}
 			}
 			sc.abund[maxtag] = abm;
@@ -788,9 +816,8 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 			// left: update == inf) the reference zeroes pair 0 without touching coverCnt and stops.
 			sc.pairAbund[updateTag] = 0;
 		}
-		supportCnt = co.bcast(supportCnt, 0);
-		deplCnt = co.bcast(deplCnt, 0);
 		co.sync();
+		deplCnt = *dcount;
 		if (supportCnt == 0) break;
 		// coverCnt bookkeeping (.cpp:1965-1973): every candidate sharing a pair that just ran dry
 		if (deplCnt > 0)

@@ -406,7 +406,7 @@ int psc_solve(psc_ctx *ctx)
 		CK(cudaMemsetAsync(ch.n_exon, 0, sizeof(int) * (size_t)nUnits, ctx->stream));
 		for (int phase = 1; phase <= 3; ++phase) {
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			KLAUNCH(5, k_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, ch, phase, st.order.as<int>(), counter, ctx->coop);
+			KLAUNCH(phase == 1 ? 5 : (phase == 2 ? 8 : 9), k_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, ch, phase, st.order.as<int>(), counter, ctx->coop);
 			++launches;
 			CK(cudaGetLastError());
 		}
@@ -494,6 +494,7 @@ int psc_solve(psc_ctx *ctx)
 		}
 		bytes += (long long)st.r_comp.size() * 40 + (long long)st.r_exon_start.size() * 8;
 		ctx->timing.kernel_bytes[5] = bytes;
+		ctx->timing.kernel_bytes[8] = bytes;
 	}
 	ctx->timing.solve_ms = ms;
 	ctx->timing.kernel_launches += launches;

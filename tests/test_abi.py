@@ -33,7 +33,7 @@ def test_shim_exports_the_same_abi():
 
 def test_struct_sizes_match_header():
     # the timing struct is the one most likely to drift
-    assert ctypes.sizeof(abi.psc_timing) == 8 + 8 + 8 + 8 + 8 * 8 * 3
+    assert ctypes.sizeof(abi.psc_timing) == 8 + 8 + 8 + 8 + 8 * 12 * 3
     assert ctypes.sizeof(abi.psc_params) == 3 * 8 + 7 * 4 + 4  # padded to 8
 
 
