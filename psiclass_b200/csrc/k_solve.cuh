@@ -86,6 +86,7 @@ struct UnitScratch {
 	int *depl;         // [M] pairs depleted in the current iteration
 	double *score;     // [A] cached ComputeScore of the candidate, -1: not selectable
 	double *contrib;   // [M] this iteration's support of maxtag per pair, -1: pair was already depleted
+	int *picked;       // [cap] candidates owning a csupport row, ascending
 	int *reach;        // [32 * n] per-lane scratch of the chain-coverage pass
 	double *persist;   // [4] inf, any-compatible flag, maxAbundance: round 1 -> round 2
 	uint64_t *tmpbits; // [4 * W]
@@ -119,6 +120,7 @@ __host__ __device__ inline size_t unit_scratch_layout(UnitScratch *o, char *base
 	s.depl = cv.take<int>((size_t)M + 1);
 	s.score = cv.take<double>((size_t)A);
 	s.contrib = cv.take<double>((size_t)M + 1);
+	s.picked = cv.take<int>((size_t)cap + 1);
 	s.reach = cv.take<int>((size_t)32 * n);
 	s.persist = cv.take<double>(4);
 	s.tmpbits = cv.take<uint64_t>((size_t)4 * W);
@@ -490,6 +492,34 @@ PSC_DEV bool pair_in_tx(const TableView &t, int j, const uint64_t *tb, int tf, i
 	       compat(tb, tf, tl, false, t.bits + (long long)b * W, t.first[b], t.last[b], W) == 1;
 }
 
+// One row of the compatibility bit-matrix (btable[i], .cpp:1426-1442): the 32 lanes test 32 mate
+// pairs at a time and a warp ballot packs the results into one 32-bit half word.
+// Returns non-zero (in every lane) if any bit of the row is set.
+PSC_DEV int build_pair_row(const Coop &co, const TableView &t, const uint64_t *tb, int tf, int tl, int W, int M, int MW,
+                           uint64_t *row)
+{
+	uint32_t *row32 = (uint32_t *)row;
+	int any = 0;
+	int n32 = 2 * MW;
+	for (int k = 0; k < n32; ++k) {
+		uint32_t mask = 0;
+		int j0 = k * 32;
+		if (co.n > 1) {
+			int j = j0 + co.lane;
+			bool in = j < M && pair_in_tx(t, j, tb, tf, tl, W);
+			mask = co.ballot(in);
+		} else {
+			for (int b = 0; b < 32; ++b) {
+				int j = j0 + b;
+				if (j < M && pair_in_tx(t, j, tb, tf, tl, W)) mask |= 1u << b;
+			}
+		}
+		if (co.lane == 0) row32[k] = mask;
+		if (mask) any = 1;
+	}
+	return any;
+}
+
 // =============================================================================================
 // PickTranscripts (TranscriptDecider.cpp:1368-2119): greedy quantitative set cover
 // round2: candidate weights use the round-1 support (alltranscripts[i].FPKM); the compatibility
@@ -525,20 +555,11 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		}
 		inf = co.max(inf);
 		inf = inf + 1;
-		// ---- compatibility matrix: lanes over 64-pair words ----
+		// ---- compatibility matrix: warp ballot over 32 pairs at a time ----
 		int anySet = 0;
-		for (int i = 0; i < A; ++i) {
-			const uint64_t *tb = cd.bits + (long long)i * W;
-			int tf = cd.first[i], tl = cd.last[i];
-			for (int w = co.lane; w < MW; w += co.n) {
-				uint64_t word = 0;
-				int jend = (w + 1) * 64 < M ? (w + 1) * 64 : M;
-				for (int j = w * 64; j < jend; ++j)
-					if (pair_in_tx(t, j, tb, tf, tl, W)) word |= (uint64_t)1 << (j & 63);
-				sc.btable[(long long)i * MW + w] = word;
-				if (word) anySet = 1;
-			}
-		}
+		for (int i = 0; i < A; ++i)
+			anySet |= build_pair_row(co, t, cd.bits + (long long)i * W, cd.first[i], cd.last[i], W, M, MW,
+			                         sc.btable + (long long)i * MW);
 		anySet = co.max(anySet);
 		co.sync();
 		if (co.lane == 0) {
@@ -707,13 +728,10 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		{
 			double lu = inf;
 			int lt = -1;
-			for (int w = co.lane; w < MW; w += co.n) {
-				uint64_t word = btm[w];
-				while (word) {
-					int j = w * 64 + ctz64(word);
-					word &= word - 1;
-					if (sc.pairAbund[j] > 0 && sc.pairAbund[j] <= lu) { lu = sc.pairAbund[j]; lt = j; }
-				}
+			for (int j = co.lane; j < M; j += co.n) {
+				if (!bt_test(btm, j)) continue;
+				double pa = sc.pairAbund[j];
+				if (pa > 0 && pa <= lu) { lu = pa; lt = j; }
 			}
 			if (co.n > 1) {
 				for (int o = 16; o > 0; o >>= 1) {
@@ -730,7 +748,12 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 			double *row = sc.pool + (long long)poolUsed * M;
 			for (int j = co.lane; j < M; j += co.n) row[j] = 0;
 			co.sync();
-			if (co.lane == 0) sc.slot[maxtag] = poolUsed;
+			if (co.lane == 0) {
+				sc.slot[maxtag] = poolUsed;
+				int q = poolUsed; // keep the owner list sorted by candidate index
+				while (q > 0 && sc.picked[q - 1] > maxtag) { sc.picked[q] = sc.picked[q - 1]; --q; }
+				sc.picked[q] = maxtag;
+			}
 			++poolUsed;
 			co.sync();
 		}
@@ -744,25 +767,21 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		// index order by phase B, so the fp64 sum keeps the reference's order.
 		{
 			int ls = 0;
-			for (int w = co.lane; w < MW; w += co.n) {
-				uint64_t word = btm[w];
-				while (word) {
-					int j = w * 64 + ctz64(word);
-					word &= word - 1;
-					double pa = sc.pairAbund[j];
-					if (pa > 0) {
-						pa -= 1 * update;
-						double factor = t.pec[j];
-						double tmp = (t.psup[j] * update / t.pnorm[j] * factor);
-						rowm[j] += tmp;
-						sc.contrib[j] = tmp;
-						if (pa <= 0) sc.depl[atomic_add(dcount, 1)] = j;
-						if (pa < 0) pa = 0;
-						sc.pairAbund[j] = pa;
-						++ls;
-					} else
-						sc.contrib[j] = -1; // depleted before this iteration: phase B looks at it
-				}
+			for (int j = co.lane; j < M; j += co.n) {
+				if (!bt_test(btm, j)) continue;
+				double pa = sc.pairAbund[j];
+				if (pa > 0) {
+					pa -= 1 * update;
+					double factor = t.pec[j];
+					double tmp = (t.psup[j] * update / t.pnorm[j] * factor);
+					rowm[j] += tmp;
+					sc.contrib[j] = tmp;
+					if (pa <= 0) sc.depl[atomic_add(dcount, 1)] = j;
+					if (pa < 0) pa = 0;
+					sc.pairAbund[j] = pa;
+					++ls;
+				} else
+					sc.contrib[j] = -1; // depleted before this iteration: phase B looks at it
 			}
 			supportCnt = co.sum(ls);
 		}
@@ -782,7 +801,10 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 					} else if (rowm[j] == 0) {
 						double takeOut = 0, factor = t.pec[j];
 						int listCnt = 0;
-						for (int i = 0; i < A; ++i) {
+						// only candidates that were picked before can have abundance > 0: walk the (index-sorted)
+						// list of row owners instead of all A candidates
+						for (int pq = 0; pq < poolUsed; ++pq) {
+							int i = sc.picked[pq];
 							if (i == maxtag) continue;
 							if (sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
 								double ci = sc.slot[i] >= 0 ? sc.pool[(long long)sc.slot[i] * M + j] : 0.0;

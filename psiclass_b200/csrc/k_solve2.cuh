@@ -41,17 +41,9 @@ PSC_DEV void abundance_em(const Coop &co, const CompView &v, const TableView &t,
 	int T = pv.T, M = t.M, W = v.W;
 	if (T <= 0) return;
 	int MW = (M + 63) >> 6;
-	for (int i = 0; i < T; ++i) {
-		const uint64_t *tb = pv.bits(i);
-		int tf = pv.first(i), tl = pv.last(i);
-		for (int w = co.lane; w < MW; w += co.n) {
-			uint64_t word = 0;
-			int jend = (w + 1) * 64 < M ? (w + 1) * 64 : M;
-			for (int j = w * 64; j < jend; ++j)
-				if (pair_in_tx(t, j, tb, tf, tl, W)) word |= (uint64_t)1 << (j & 63);
-			sc.ebtable[(long long)i * MW + w] = word;
-		}
-	}
+	for (int i = 0; i < T; ++i)
+		build_pair_row(co, t, pv.bits(i), pv.first(i), pv.last(i), W, M, MW, sc.ebtable + (long long)i * MW);
+	co.sync();
 	for (int i = co.lane; i < T; i += co.n) {
 		int len = tx_len(v, pv.bits(i), pv.first(i), pv.last(i));
 		int L = len - prm.fragLen + 2 * prm.fragStdev;

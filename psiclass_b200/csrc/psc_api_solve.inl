@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const
 }
 
 // phase: 1 pick round 1, 2 pick round 2 + filtration, 3 rescue
-__global__ void __launch_bounds__(128) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *order, int *counter,
+__global__ void __launch_bounds__(128, 4) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *order, int *counter,
                                                int width)
 {
 	Coop co = make_coop(width);
@@ -322,9 +322,9 @@ int psc_solve(psc_ctx *ctx)
 				return ctx->fail("out of device memory");
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
 			{
-				const int smemPerWarp = ctx->coop == 32 ? 24 * 1024 : 0; // 4 warps -> 96 KB per CTA, 2 CTAs per SM
+				const int smemPerWarp = ctx->coop == 32 ? 16 * 1024 : 0; // 4 warps -> 64 KB per CTA, 3 CTAs per SM
 #ifndef PSC_CPU_SHIM
-				CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 24 * 1024));
+				CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16 * 1024));
 				ctx->ktime_begin(4);
 				k_dp_units<<<launch_grid(ctx, nUnits), 128, 4 * smemPerWarp, ctx->stream>>>(
 				    ctx->gd, sv, st.dp_units.as<DpUnit>(), st.order.as<int>(), nUnits, (char *)st.scratch.p, (char *)st.dp_tx.p,
