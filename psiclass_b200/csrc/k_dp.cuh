@@ -31,7 +31,8 @@ struct DpScratch {
 	int *P;         // the path stack: solve keys and search extensions share it
 	int *fr;        // frames
 	double *fdcover;
-	int *fdmeta; // first,last,strand per solve frame
+	int *fdmeta; // first,last,strand,#uncovered edges inside the key: per solve frame
+	int *tcEnd;  // [n+1] number of constraints whose .first <= q
 	uint64_t *fdbits;
 	int *ext;
 	int extCap;
@@ -77,7 +78,8 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 	s.P = cv.take<int>((size_t)n + 4);
 	s.fr = cv.take<int>((size_t)(2 * n + 6) * PSC_FR_INTS);
 	s.fdcover = cv.take<double>((size_t)n + 3);
-	s.fdmeta = cv.take<int>((size_t)(n + 3) * 3);
+	s.fdmeta = cv.take<int>((size_t)(n + 3) * 4);
+	s.tcEnd = cv.take<int>((size_t)n + 2);
 	s.fdbits = cv.take<uint64_t>((size_t)(n + 3) * W);
 	long long ec = (long long)(n + 2) * (Cmax + 1);
 	if (ec > (long long)4 << 20) ec = (long long)4 << 20;
@@ -133,13 +135,37 @@ PSC_DEV bool dp_edge_uncovered(const DpState &st, int a, int b)
 // first index >= from whose constraint starts after `bound` (constraints are sorted by .first)
 PSC_DEV int dp_tc_end(const DpState &st, int from, int bound)
 {
-	int lo = from, hi = st.d.tcCnt;
-	while (lo < hi) {
-		int mid = (lo + hi) >> 1;
-		if (st.d.tcf[mid] <= bound) lo = mid + 1;
-		else hi = mid;
+	int e = bound >= st.v.n - 1 ? st.d.tcCnt : (bound < 0 ? 0 : st.d.tcEnd[bound]);
+	return e > from ? e : from;
+}
+
+// sub = [base |] bits(p1) | bits(p2).  For components of <= 128 subexons every lane keeps its own copy
+// in registers (no shared buffer, no synchronisation); wider ones go through the shared buffer.
+PSC_DEV void dp_build_sub(const DpState &st, uint64_t *sub, const uint64_t *base, const int *p1, int n1, const int *p2, int n2)
+{
+	if (st.W <= 2) {
+		uint64_t a = base ? base[0] : 0, b = (base && st.W == 2) ? base[1] : 0;
+		for (int i = 0; i < n1; ++i) {
+			int x = p1[i];
+			if (x < 64) a |= (uint64_t)1 << x;
+			else b |= (uint64_t)1 << (x - 64);
+		}
+		for (int i = 0; i < n2; ++i) {
+			int x = p2[i];
+			if (x < 64) a |= (uint64_t)1 << x;
+			else b |= (uint64_t)1 << (x - 64);
+		}
+		sub[0] = a;
+		if (st.W == 2) sub[1] = b;
+		return;
 	}
-	return lo;
+	st.co.sync();
+	if (st.co.lane == 0) {
+		for (int w = 0; w < st.W; ++w) sub[w] = base ? base[w] : 0;
+		for (int i = 0; i < n1; ++i) bt_set(sub, p1[i]);
+		for (int i = 0; i < n2; ++i) bt_set(sub, p2[i]);
+	}
+	st.co.sync();
 }
 
 // the three cover scans of the reference (.cpp:463-490, 569-596, 732-755), lane-parallel.
@@ -148,31 +174,31 @@ PSC_DEV double dp_scan_cover(const DpState &st, const uint64_t *tb, int tf, int 
                              bool &belowMin)
 {
 	int end = dp_tc_end(st, tcStart, bound);
-	int below = 0, cnt = 0;
+	if (end <= tcStart) return cover; // nothing starts inside the range: no lane has work, no reduction
+	bool below = false;
+	int cnt = 0;
 	double mn = 1e300;
 	for (int i = tcStart + st.co.lane; i < end; i += st.co.n) {
 		if (compat(tb, tf, tl, false, st.d.tcb + (long long)i * st.W, st.d.tcf[i], st.d.tcl[i], st.W) != 1) continue;
-		if (st.d.tcnorm[i] <= st.minAbundance) { below = 1; continue; }
+		if (st.d.tcnorm[i] <= st.minAbundance) { below = true; continue; }
 		if (st.d.tcab[i] <= 0) continue;
 		++cnt;
 		if (st.d.tcnorm[i] < mn) mn = st.d.tcnorm[i];
 	}
-	// a below-minimum constraint only counts if no earlier one... no: the reference breaks at the FIRST
-	// compatible constraint with normAbund <= minAbundance, whatever was counted before, and returns -2
-	below = st.co.max(below);
-	if (below) {
+	// the reference breaks at the FIRST compatible constraint with normAbund <= minAbundance, whatever
+	// was counted before, and returns -2: "any" is enough
+	if (st.co.any(below)) {
 		belowMin = true;
 		return -2;
 	}
+	cnt = st.co.sum(cnt);
 	if (st.forAbundance) {
-		mn = st.co.min(mn);
-		cnt = st.co.sum(cnt);
 		if (cnt > 0) {
+			mn = st.co.min_nonneg(mn);
 			if (cover == 0 || mn < cover) cover = mn;
 		}
 		return cover;
 	}
-	cnt = st.co.sum(cnt);
 	return cover + cnt;
 }
 
@@ -209,7 +235,8 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 	int W = st.W;
 	int sp = 0, extTop = 0, dpTop = 0;
 	long long ret = -1;
-	uint64_t *sub = d.work + 2 * W; // the reference's attr.bufferTxpt
+	uint64_t subl[2];
+	uint64_t *sub = W <= 2 ? subl : d.work + 2 * W; // the reference's attr.bufferTxpt
 	// push root
 	co.sync();
 	if (co.lane == 0) {
@@ -254,21 +281,17 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				}
 				// ---- fresh evaluation ----
 				int tcStart = FR(fi, 5);
-				{
-					int lo = tcStart, hi = d.tcCnt;
-					while (lo < hi) { // first constraint with first >= visit[0]
-						int mid = (lo + hi) >> 1;
-						if (d.tcf[mid] < visit[0]) lo = mid + 1;
-						else hi = mid;
-					}
-					tcStart = lo;
+				{ // first constraint with first >= visit[0]
+					int lo = visit[0] > 0 ? d.tcEnd[visit[0] - 1] : 0;
+					if (lo > tcStart) tcStart = lo;
 				}
+				int keyUncov = 0;
+				for (int i = 0; i + 1 < vcnt; ++i)
+					if (dp_edge_uncovered(st, visit[i], visit[i + 1])) ++keyUncov;
 				int slot = dpTop++;
 				uint64_t *vb = d.fdbits + (long long)slot * W;
 				int last = visit[vcnt - 1];
-				co.sync();
-				dp_bits_from_path(st, sub, visit, vcnt, true);
-				co.sync();
+				dp_build_sub(st, sub, nullptr, visit, vcnt, nullptr, 0);
 				double cover = -1;
 				if (st.ce[last]) {
 					bool bm = false;
@@ -305,9 +328,10 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				if (co.lane == 0) {
 					for (int w = 0; w < W; ++w) vb[w] = sub[w];
 					d.fdcover[slot] = cover;
-					d.fdmeta[slot * 3 + 0] = visit[0];
-					d.fdmeta[slot * 3 + 1] = last;
-					d.fdmeta[slot * 3 + 2] = strand;
+					d.fdmeta[slot * 4 + 0] = visit[0];
+					d.fdmeta[slot * 4 + 1] = last;
+					d.fdmeta[slot * 4 + 2] = strand;
+					d.fdmeta[slot * 4 + 3] = keyUncov;
 					FR(fi, 1) = 1;
 					FR(fi, 5) = tcStart;
 					FR(fi, 6) = extBase;
@@ -347,9 +371,9 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				if (co.lane == 0) {
 					const uint64_t *vb = d.fdbits + (long long)slot * W;
 					for (int w = 0; w < W; ++w) mbits[w] = vb[w];
-					me->first = d.fdmeta[slot * 3 + 0];
-					me->last = d.fdmeta[slot * 3 + 1];
-					me->strand = d.fdmeta[slot * 3 + 2];
+					me->first = d.fdmeta[slot * 4 + 0];
+					me->last = d.fdmeta[slot * 4 + 1];
+					me->strand = d.fdmeta[slot * 4 + 2];
 					me->cover = d.fdcover[slot];
 					me->cnt = vcnt;
 					me->minAbundance = st.minAbundance;
@@ -373,14 +397,13 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 		if (state == 0) {
 			int vcnt = FR(fi, 5) + 1;
 			int extCnt = FR(fi, 6);
+			// uncovered edges on the walk so far (kept per frame instead of rescanning the path)
+			int walkUncov = vcnt == 1 ? d.fdmeta[oslot * 4 + 3] : FR(fi - 1, 9);
+			if (dp_edge_uncovered(st, vcnt == 1 ? parents[pcnt - 1] : visit[vcnt - 2], tag)) ++walkUncov;
 			co.sync();
-			if (co.lane == 0) {
-				visit[vcnt - 1] = tag;
-				for (int w = 0; w < W; ++w) sub[w] = 0;
-				for (int i = 0; i < pcnt; ++i) bt_set(sub, parents[i]);
-				for (int i = 0; i < vcnt; ++i) bt_set(sub, visit[i]);
-			}
+			if (co.lane == 0) visit[vcnt - 1] = tag;
 			co.sync();
+			dp_build_sub(st, sub, nullptr, parents, pcnt, visit, vcnt);
 			// drop the pending extensions that no longer fit (.cpp:407-412)
 			{
 				const int *ext = d.ext + FR(owner, 6);
@@ -401,6 +424,7 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				FR(fi, 5) = vcnt;
 				FR(fi, 6) = extCnt;
 				FR(fi, 8) = solveHere ? 0 : 1; // keepSearch
+				FR(fi, 9) = walkUncov;
 				FR(fi, 1) = 1;
 			}
 			if (solveHere) {
@@ -433,22 +457,8 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 			bool belowMin = false;
 			if (vcover >= 0) {
 				double cover = vcover;
-				co.sync();
-				if (co.lane == 0) {
-					for (int w = 0; w < W; ++w) sub[w] = vbits[w];
-					for (int i = 0; i < pcnt; ++i) bt_set(sub, parents[i]);
-				}
-				co.sync();
-				if (!st.forAbundance && st.minAbundance > 0) {
-					for (int i = 0; i < pcnt - 1; ++i)
-						if (dp_edge_uncovered(st, parents[i], parents[i + 1])) belowMin = true;
-					for (int i = -1; i < vcnt - 1; ++i) {
-						if (i == -1 && pcnt >= 1) {
-							if (dp_edge_uncovered(st, parents[pcnt - 1], visit[0])) belowMin = true;
-						} else if (dp_edge_uncovered(st, visit[i], visit[i + 1]))
-							belowMin = true;
-					}
-				}
+				dp_build_sub(st, sub, vbits, parents, pcnt, nullptr, 0);
+				if (!st.forAbundance && st.minAbundance > 0 && FR(fi, 9) > 0) belowMin = true;
 				bool bm2 = false;
 				cover = dp_scan_cover(st, sub, parents[0], vlast, tcStart, parents[pcnt - 1], cover, bm2);
 				if (bm2) belowMin = true;
@@ -458,9 +468,9 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 					if (co.lane == 0) {
 						d.fdcover[oslot] = takeBelow ? -2 : cover;
 						for (int w = 0; w < W; ++w) pb[w] = sub[w];
-						d.fdmeta[oslot * 3 + 0] = parents[0];
-						d.fdmeta[oslot * 3 + 1] = vlast;
-						d.fdmeta[oslot * 3 + 2] = strand;
+						d.fdmeta[oslot * 4 + 0] = parents[0];
+						d.fdmeta[oslot * 4 + 1] = vlast;
+						d.fdmeta[oslot * 4 + 2] = strand;
 					}
 					co.sync();
 					pcover = takeBelow ? -2 : cover;
@@ -471,9 +481,9 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 					for (int w = 0; w < W; ++w) pb[w] = vbits[w];
 					for (int i = 0; i < pcnt; ++i) bt_set(pb, parents[i]);
 					d.fdcover[oslot] = -2;
-					d.fdmeta[oslot * 3 + 0] = parents[0];
-					d.fdmeta[oslot * 3 + 1] = vlast;
-					d.fdmeta[oslot * 3 + 2] = strand;
+					d.fdmeta[oslot * 4 + 0] = parents[0];
+					d.fdmeta[oslot * 4 + 1] = vlast;
+					d.fdmeta[oslot * 4 + 2] = strand;
 				}
 				co.sync();
 				pcover = -2;
@@ -481,23 +491,10 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 			// the path may also stop at this subexon (.cpp:524-614)
 			if (st.ce[tag] && (vcover < 0 || st.forAbundance)) {
 				bool below = false;
-				co.sync();
-				if (co.lane == 0) {
-					for (int w = 0; w < W; ++w) sub[w] = 0;
-					for (int i = 0; i < pcnt; ++i) bt_set(sub, parents[i]);
-					for (int i = 0; i < vcnt; ++i) bt_set(sub, visit[i]);
-				}
-				co.sync();
+				dp_build_sub(st, sub, nullptr, parents, pcnt, visit, vcnt);
 				double cover = 0;
 				if (st.forAbundance || st.minAbundance > 0) {
-					for (int i = 0; i < pcnt - 1; ++i)
-						if (dp_edge_uncovered(st, parents[i], parents[i + 1])) below = true;
-					for (int i = -1; i < vcnt - 1; ++i) {
-						if (i == -1 && pcnt >= 1) {
-							if (dp_edge_uncovered(st, parents[pcnt - 1], visit[0])) below = true;
-						} else if (dp_edge_uncovered(st, visit[i], visit[i + 1]))
-							below = true;
-					}
+					if (FR(fi, 9) > 0) below = true;
 					if (st.forAbundance && below) cover = 1e-6;
 				}
 				bool bm2 = false;
@@ -509,9 +506,9 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 					if (co.lane == 0) {
 						d.fdcover[oslot] = takeBelow ? -2 : cover;
 						for (int w = 0; w < W; ++w) pb[w] = sub[w];
-						d.fdmeta[oslot * 3 + 0] = parents[0];
-						d.fdmeta[oslot * 3 + 1] = visit[vcnt - 1];
-						d.fdmeta[oslot * 3 + 2] = strand;
+						d.fdmeta[oslot * 4 + 0] = parents[0];
+						d.fdmeta[oslot * 4 + 1] = visit[vcnt - 1];
+						d.fdmeta[oslot * 4 + 2] = strand;
 					}
 					co.sync();
 				}
@@ -588,6 +585,17 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 	int W = st.W, n = v.n, tcCnt = d.tcCnt;
 	st.timeStamp = 1;
 	++st.epoch;
+	// tcEnd[q] = number of constraints starting at or before subexon q (they are sorted by .first)
+	for (int q = co.lane; q < n; q += co.n) {
+		int lo = 0, hi = tcCnt;
+		while (lo < hi) {
+			int mid = (lo + hi) >> 1;
+			if (d.tcf[mid] <= q) lo = mid + 1;
+			else hi = mid;
+		}
+		d.tcEnd[q] = lo;
+	}
+	co.sync();
 	// ---- uncovered edges (.cpp:890-947): lanes over edges ----
 	{
 		int e0 = v.noff[0];
@@ -902,7 +910,7 @@ PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
 	int *P = cv.take<int>((size_t)n + 4);
 	int *fr = cv.take<int>((size_t)(2 * n + 6) * PSC_FR_INTS);
 	double *fdcover = cv.take<double>((size_t)n + 3);
-	int *fdmeta = cv.take<int>((size_t)(n + 3) * 3);
+	int *fdmeta = cv.take<int>((size_t)(n + 3) * 4);
 	uint64_t *fdbits = cv.take<uint64_t>((size_t)(n + 3) * W);
 	uint64_t *work = cv.take<uint64_t>((size_t)8 * W);
 	if (cv.off > smBytes) return;

@@ -63,11 +63,11 @@ struct Coop {
 	PSC_DEV bool any(bool p) const { return ballot(p) != 0; }
 	PSC_DEV int rank_in(uint32_t mask) const { return popc32(mask & ((1u << lane) - 1u)); }
 
+	// 32-bit reductions use the warp-reduce unit (REDUX, sm_80+): one instruction instead of five shuffles
 	PSC_DEV int sum(int v) const
 	{
 #ifndef PSC_CPU_SHIM
-		if (n > 1)
-			for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		if (n > 1) return __reduce_add_sync(0xffffffffu, v);
 #endif
 		return v;
 	}
@@ -82,22 +82,29 @@ struct Coop {
 	PSC_DEV int max(int v) const
 	{
 #ifndef PSC_CPU_SHIM
-		if (n > 1)
-			for (int o = 16; o > 0; o >>= 1) {
-				int t = __shfl_xor_sync(0xffffffffu, v, o);
-				v = t > v ? t : v;
-			}
+		if (n > 1) return __reduce_max_sync(0xffffffffu, v);
 #endif
 		return v;
 	}
 	PSC_DEV int min(int v) const
 	{
 #ifndef PSC_CPU_SHIM
-		if (n > 1)
-			for (int o = 16; o > 0; o >>= 1) {
-				int t = __shfl_xor_sync(0xffffffffu, v, o);
-				v = t < v ? t : v;
-			}
+		if (n > 1) return __reduce_min_sync(0xffffffffu, v);
+#endif
+		return v;
+	}
+	// minimum of NON-NEGATIVE doubles: their bit patterns order like the values, so two 32-bit
+	// warp reductions (high word, then low word among the lanes that hold the smallest high word) do it
+	PSC_DEV double min_nonneg(double v) const
+	{
+#ifndef PSC_CPU_SHIM
+		if (n > 1) {
+			unsigned long long b = (unsigned long long)__double_as_longlong(v);
+			unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+			unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+			unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+			return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+		}
 #endif
 		return v;
 	}

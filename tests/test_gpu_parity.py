@@ -18,6 +18,8 @@ CONFIGS = [
     dict(seed=14, n_genes=100, n_samples=3, single_end=1),
     dict(seed=15, n_genes=100, n_samples=6, p_paralog=0.15, stranded=1),
     dict(seed=47, n_genes=30, n_samples=3, mean_pairs=0.3, exon_min=1, exon_max=2),
+    # ~146 subexons per component: three 64-bit words per bit vector, DP path, int32 path-count overflow (Q4)
+    dict(seed=20, n_genes=4, n_samples=3, exon_mu=4.8, exon_sigma=0.1, exon_min=110, exon_max=120, iso_lambda=2.0, p_alt=0.3, mean_pairs=150.0),
 ]
 
 

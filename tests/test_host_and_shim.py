@@ -16,6 +16,8 @@ CLASSES_SHIM = os.path.join(ROOT, "tests", "shim", "_build", "classes_shim")
     dict(seed=42, n_genes=30, n_samples=4, mean_pairs=200.0, exon_mu=2.2, iso_lambda=4.0, p_alt=0.3, p_ir=0.1),
     dict(seed=43, n_genes=40, n_samples=2, single_end=1),
     dict(seed=44, n_genes=40, n_samples=5, p_paralog=0.15, stranded=1, name_style=2, p_noise=0.1, p_overlap=0.15),
+    # ~146 subexons per component: three 64-bit words per bit vector, DP path, int32 path-count overflow (Q4)
+    dict(seed=20, n_genes=4, n_samples=3, exon_mu=4.8, exon_sigma=0.1, exon_min=110, exon_max=120, iso_lambda=2.0, p_alt=0.3, mean_pairs=150.0),
 ])
 def test_kernel_logic_matches_oracle_on_cpu_shim(cfg):
     wl = testkit.Workload.synth(threads=4, **cfg)
