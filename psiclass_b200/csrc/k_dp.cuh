@@ -123,6 +123,7 @@ struct DpState {
 	double minAbundance;
 	int timeStamp, epoch;
 	int *err;
+	long long nStates, nLevels, nIters; // instrumentation (PSC_DEBUG_DP)
 };
 
 PSC_DEV bool dp_edge_uncovered(const DpState &st, int a, int b)
@@ -256,21 +257,19 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 			DpMemo *me = d.ent + mi;
 			uint64_t *mbits = d.ebits + mi * W;
 			if (state == 0) {
+				// bits of the key (needed for the hash probe and, on a miss, as the start of the path)
+				dp_build_sub(st, sub, nullptr, visit, vcnt, nullptr, 0);
 				// ---- memo probe (.cpp:652-706) ----
 				bool hit = false;
 				if (me->epoch == st.epoch && me->cover != -1 && me->strand == strand &&
 				    (me->timeStamp == st.timeStamp || (me->minAbundance < st.minAbundance && me->cover == -2))) {
 					if (vcnt <= 2) hit = true;
 					else if (me->cnt == vcnt && me->first == visit[0]) {
-						// the first vcnt subexons of the stored path must be this key
+						// the stored path restricted to [visit[0], visit[vcnt-1]] must be exactly this key
 						bool same = true;
 						int lo = visit[0], hi = visit[vcnt - 1];
-						int k = 0;
-						for (int q = lo; q <= hi && same; ++q) {
-							bool inKey = k < vcnt && visit[k] == q;
-							if (inKey) ++k;
-							if (bt_test(mbits, q) != inKey) same = false;
-						}
+						for (int w = lo >> 6; w <= (hi >> 6) && same; ++w)
+							if ((mbits[w] & keep_mask(w, lo, hi)) != sub[w]) same = false;
 						hit = same;
 					}
 				}
@@ -280,6 +279,7 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 					continue;
 				}
 				// ---- fresh evaluation ----
+				++st.nStates;
 				int tcStart = FR(fi, 5);
 				{ // first constraint with first >= visit[0]
 					int lo = visit[0] > 0 ? d.tcEnd[visit[0] - 1] : 0;
@@ -291,7 +291,6 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				int slot = dpTop++;
 				uint64_t *vb = d.fdbits + (long long)slot * W;
 				int last = visit[vcnt - 1];
-				dp_build_sub(st, sub, nullptr, visit, vcnt, nullptr, 0);
 				double cover = -1;
 				if (st.ce[last]) {
 					bool bm = false;
@@ -316,13 +315,31 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 						extCnt = d.extCap - extBase;
 					}
 					co.sync();
-					// stable sort by .last (.cpp:781-796; glibc qsort == merge sort): insertion sort, lists are short
-					if (co.lane == 0)
-						for (int a = 1; a < extCnt; ++a) {
-							int x = d.ext[extBase + a], xl = d.tcl[x], b = a - 1;
-							while (b >= 0 && d.tcl[d.ext[extBase + b]] > xl) { d.ext[extBase + b + 1] = d.ext[extBase + b]; --b; }
-							d.ext[extBase + b + 1] = x;
+					// stable sort by .last (.cpp:781-796; glibc qsort == merge sort): every lane ranks its
+					// elements (count of smaller keys, ties by position) and scatters them into the free space
+					// above the list, which is then copied back
+					if (extCnt > 1) {
+						int *src = d.ext + extBase, *tmp = src + extCnt;
+						if (extBase + 2 * extCnt <= d.extCap) {
+							for (int a = co.lane; a < extCnt; a += co.n) {
+								int x = src[a], xl = d.tcl[x], r = 0;
+								for (int b = 0; b < extCnt; ++b) {
+									int yl = d.tcl[src[b]];
+									if (yl < xl || (yl == xl && b < a)) ++r;
+								}
+								tmp[r] = x;
+							}
+							co.sync();
+							for (int a = co.lane; a < extCnt; a += co.n) src[a] = tmp[a];
+							co.sync();
+						} else if (co.lane == 0) {
+							for (int a = 1; a < extCnt; ++a) {
+								int x = src[a], xl = d.tcl[x], b = a - 1;
+								while (b >= 0 && d.tcl[src[b]] > xl) { src[b + 1] = src[b]; --b; }
+								src[b + 1] = x;
+							}
 						}
+					}
 				}
 				extTop = extBase + extCnt;
 				if (co.lane == 0) {
@@ -649,6 +666,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 			} else {
 				maxCover.cover = -1;
 				++st.timeStamp;
+				++st.nLevels;
 				for (int i = 0; i < n; ++i) {
 					if (!st.cs[i]) continue;
 					long long r = dp_solve_root(st, i);
@@ -751,6 +769,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 			co.sync();
 		}
 		++iterCnt;
+		++st.nIters;
 		if (iterCnt >= iterBound) break;
 	}
 	(void)sub;
@@ -923,9 +942,11 @@ PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
 }
 
 PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv, const DpUnit &u, char *scratchBase,
-                           char *txBase, int *n_tx_out, char *sm, size_t smBytes)
+                           char *txBase, int *n_tx_out, char *sm, size_t smBytes, long long *dbg)
 {
 	DpState st;
+	st.nStates = st.nLevels = st.nIters = 0;
+	long long t0 = clock64();
 	st.co = co;
 	st.v = comp_view(g, u.comp);
 	const CompView &v = st.v;
@@ -985,6 +1006,12 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 	co.sync();
 	int nt = dp_pick(st, u.iterBound);
 	if (co.lane == 0) *n_tx_out = nt;
+	if (dbg && co.lane == 0) {
+		dbg[0] = clock64() - t0;
+		dbg[1] = st.nStates;
+		dbg[2] = st.nLevels;
+		dbg[3] = st.nIters;
+	}
 	co.sync();
 }
 

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) k_enumerate(GraphDev g, SolveDev sv, cons
 }
 
 __global__ void __launch_bounds__(128) k_dp_units(GraphDev g, SolveDev sv, const DpUnit *units, const int *order, int nUnits,
-                                                  char *scratch, char *txArena, int *n_tx, int *counter, int width, int smemPerWarp)
+                                                  char *scratch, char *txArena, int *n_tx, int *counter, int width, int smemPerWarp, long long *dbg)
 {
 	Coop co = make_coop(width);
 	char *sm = nullptr;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) k_dp_units(GraphDev g, SolveDev sv, const
 		u = co.bcast(u, 0);
 		if (u >= nUnits) break;
 		int ui = order[u];
-		dp_unit_pick(co, g, sv, units[ui], scratch, txArena, n_tx + ui, sm, smBytes);
+		dp_unit_pick(co, g, sv, units[ui], scratch, txArena, n_tx + ui, sm, smBytes, dbg ? dbg + 4 * (long long)ui : nullptr);
 		co.sync();
 	}
 }
@@ -246,6 +246,7 @@ int psc_solve(psc_ctx *ctx)
 		CK(cudaStreamSynchronize(ctx->stream)); // enumList staging buffer is reused below
 	}
 	// ---- P2b: DP.  Units are (component, sample); chunks of components that fit the memory budget ----
+	long long dpBytes = 0;
 	{
 		size_t i0 = 0;
 		while (i0 < dpList.size()) {
@@ -297,6 +298,8 @@ int psc_solve(psc_ctx *ctx)
 				}
 				if (i1 > i0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
 				for (auto &u : mine) {
+					// algorithmic bytes of the DP kernel: the sample's constraint table read once, its transcript list written once
+					dpBytes += (long long)ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] * (8LL * W + 40) + (long long)u.iterBound * (8LL * W + 8);
 					units.push_back(u);
 					cost.push_back((long long)u.iterBound * (ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] + 1));
 				}
@@ -323,16 +326,23 @@ int psc_solve(psc_ctx *ctx)
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
 			{
 				const int smemPerWarp = ctx->coop == 32 ? 16 * 1024 : 0; // 4 warps -> 64 KB per CTA, 3 CTAs per SM
+				long long *dbgPtr = nullptr;
+				const bool dbgOn = getenv("PSC_DEBUG_DP") != nullptr;
+				if (dbgOn) {
+					if (!st.dp_dbg.ensure(sizeof(long long) * 4 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
+					CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 4 * (size_t)(nUnits + 1), ctx->stream));
+					dbgPtr = st.dp_dbg.as<long long>();
+				}
 #ifndef PSC_CPU_SHIM
 				CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16 * 1024));
 				ctx->ktime_begin(4);
 				k_dp_units<<<launch_grid(ctx, nUnits), 128, 4 * smemPerWarp, ctx->stream>>>(
 				    ctx->gd, sv, st.dp_units.as<DpUnit>(), st.order.as<int>(), nUnits, (char *)st.scratch.p, (char *)st.dp_tx.p,
-				    st.dp_ntx.as<int>(), counter, ctx->coop, smemPerWarp);
+				    st.dp_ntx.as<int>(), counter, ctx->coop, smemPerWarp, dbgPtr);
 				ctx->ktime_end();
 #else
 				KLAUNCH(4, k_dp_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, st.dp_units.as<DpUnit>(), st.order.as<int>(), nUnits,
-				        (char *)st.scratch.p, (char *)st.dp_tx.p, st.dp_ntx.as<int>(), counter, ctx->coop, smemPerWarp);
+				        (char *)st.scratch.p, (char *)st.dp_tx.p, st.dp_ntx.as<int>(), counter, ctx->coop, smemPerWarp, dbgPtr);
 #endif
 			}
 			++launches;
@@ -343,6 +353,23 @@ int psc_solve(psc_ctx *ctx)
 			++launches;
 			CK(cudaGetLastError());
 			CK(cudaStreamSynchronize(ctx->stream));
+			if (getenv("PSC_DEBUG_DP")) {
+				std::vector<long long> h((size_t)nUnits * 4);
+				cudaMemcpy(h.data(), st.dp_dbg.p, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+				std::vector<int> ix((size_t)nUnits);
+				for (int u = 0; u < nUnits; ++u) ix[(size_t)u] = u;
+				std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 4] > h[(size_t)b * 4]; });
+				long long tot = 0;
+				for (int u = 0; u < nUnits; ++u) tot += h[(size_t)u * 4];
+				fprintf(stderr, "[dp] %d units, total %.1f Mcycles\n", nUnits, tot / 1e6);
+				for (int k = 0; k < 12 && k < nUnits; ++k) {
+					int u = ix[(size_t)k];
+					int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
+					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld\n", u, c, s,
+					        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
+					        h[(size_t)u * 4] / 1e6, h[(size_t)u * 4 + 1], h[(size_t)u * 4 + 2], h[(size_t)u * 4 + 3]);
+				}
+			}
 			i0 = i1;
 		}
 	}
@@ -495,6 +522,7 @@ int psc_solve(psc_ctx *ctx)
 		bytes += (long long)st.r_comp.size() * 40 + (long long)st.r_exon_start.size() * 8;
 		ctx->timing.kernel_bytes[5] = bytes;
 		ctx->timing.kernel_bytes[8] = bytes;
+		ctx->timing.kernel_bytes[4] = dpBytes;
 	}
 	ctx->timing.solve_ms = ms;
 	ctx->timing.kernel_launches += launches;
