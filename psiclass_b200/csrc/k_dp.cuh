@@ -13,7 +13,11 @@ namespace pscdev {
 
 struct DpMemo {
 	double cover, minAbundance;
+	// smallest normAbund among the constraints compatible with the stored path (those the recursion
+	// examined): the entry stays exact for every higher threshold below it, see dp_memo_hit
+	double beta;
 	int first, last, cnt, timeStamp, strand, epoch;
+	int iter, mode; // outer iteration / forAbundance flag the entry was computed under
 };
 
 struct DpScratch {
@@ -30,7 +34,7 @@ struct DpScratch {
 	uint8_t *uncov; // per next-edge of the component
 	int *P;         // the path stack: solve keys and search extensions share it
 	int *fr;        // frames
-	double *fdcover;
+	double *fdcover, *fdbeta;
 	int *fdmeta; // first,last,strand,#uncovered edges inside the key: per solve frame
 	int *tcEnd;  // [n+1] number of constraints whose .first <= q
 	uint64_t *fdbits;
@@ -78,6 +82,7 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 	s.P = cv.take<int>((size_t)n + 4);
 	s.fr = cv.take<int>((size_t)(2 * n + 6) * PSC_FR_INTS);
 	s.fdcover = cv.take<double>((size_t)n + 3);
+	s.fdbeta = cv.take<double>((size_t)n + 3);
 	s.fdmeta = cv.take<int>((size_t)(n + 3) * 4);
 	s.tcEnd = cv.take<int>((size_t)n + 2);
 	s.fdbits = cv.take<uint64_t>((size_t)(n + 3) * W);
@@ -121,9 +126,9 @@ struct DpState {
 	int W;
 	bool forAbundance;
 	double minAbundance;
-	int timeStamp, epoch;
+	int timeStamp, epoch, iter;
 	int *err;
-	long long nStates, nLevels, nIters; // instrumentation (PSC_DEBUG_DP)
+	long long nStates, nLevels, nIters, nFrames, nRoots, cycRoot, cycAssign; // instrumentation (PSC_DEBUG_DP)
 };
 
 PSC_DEV bool dp_edge_uncovered(const DpState &st, int a, int b)
@@ -172,16 +177,18 @@ PSC_DEV void dp_build_sub(const DpState &st, uint64_t *sub, const uint64_t *base
 // the three cover scans of the reference (.cpp:463-490, 569-596, 732-755), lane-parallel.
 // All reductions are order-free: a count of integers, a minimum, or "any".
 PSC_DEV double dp_scan_cover(const DpState &st, const uint64_t *tb, int tf, int tl, int tcStart, int bound, double cover,
-                             bool &belowMin)
+                             bool &belowMin, double &beta)
 {
 	int end = dp_tc_end(st, tcStart, bound);
 	if (end <= tcStart) return cover; // nothing starts inside the range: no lane has work, no reduction
 	bool below = false;
-	int cnt = 0;
-	double mn = 1e300;
+	int cnt = 0, ccnt = 0;
+	double mn = 1e300, mnAll = 1e300;
 	for (int i = tcStart + st.co.lane; i < end; i += st.co.n) {
 		if (compat(tb, tf, tl, false, st.d.tcb + (long long)i * st.W, st.d.tcf[i], st.d.tcl[i], st.W) != 1) continue;
 		if (st.d.tcnorm[i] <= st.minAbundance) { below = true; continue; }
+		++ccnt;
+		if (st.d.tcnorm[i] < mnAll) mnAll = st.d.tcnorm[i];
 		if (st.d.tcab[i] <= 0) continue;
 		++cnt;
 		if (st.d.tcnorm[i] < mn) mn = st.d.tcnorm[i];
@@ -191,6 +198,11 @@ PSC_DEV double dp_scan_cover(const DpState &st, const uint64_t *tb, int tf, int 
 	if (st.co.any(below)) {
 		belowMin = true;
 		return -2;
+	}
+	// beta: smallest normAbund among the compatible constraints, depleted ones included
+	if (!st.forAbundance && st.co.sum(ccnt) > 0) {
+		mnAll = st.co.min_nonneg(mnAll);
+		if (mnAll < beta) beta = mnAll;
 	}
 	cnt = st.co.sum(cnt);
 	if (st.forAbundance) {
@@ -212,13 +224,31 @@ PSC_DEV void dp_bits_from_path(const DpState &st, uint64_t *dst, const int *p, i
 	for (int i = 0; i < cnt; ++i) bt_set(dst, p[i]);
 }
 
+#define PSC_DP_HASH 8191u
 PSC_DEV long long dp_memo_index(const DpState &st, const int *visit, int vcnt)
 {
 	if (vcnt == 1) return visit[0];
 	if (vcnt == 2) return st.d.f2Base + (long long)visit[0] * st.v.n + visit[1]; // seCnt <= 10000 is enforced by the host
-	long long key = 0;
-	for (int i = 0; i < vcnt; ++i) key = (key * st.v.n + visit[i]) % st.d.hashMax;
+	// key < 8191 and seCnt <= 10000: the products fit 32 bits, and the modulus is a compile-time constant
+	uint32_t key = 0, n = (uint32_t)st.v.n;
+	for (int i = 0; i < vcnt; ++i) key = (key * n + (uint32_t)visit[i]) % PSC_DP_HASH;
 	return st.d.hashBase + key;
+}
+
+// Memo validity.  The reference accepts an entry computed in the current pass (timeStamp) or a failed
+// one (-2) from a lower threshold (.cpp:654-656).  Additionally an entry with a real path computed
+// earlier in the SAME outer iteration under a lower positive threshold is bit-identical to what a
+// recomputation would give as long as no constraint on its path is at or below the new threshold:
+// raising minAbundance only removes candidates or lowers their value, abundances do not change inside
+// an iteration, and the uncovered-edge rule is the same for every positive threshold -- so the winner
+// of the left fold (first maximum) is unchanged.  This saves most of the per-threshold recomputation.
+PSC_DEV bool dp_memo_hit(const DpState &st, const DpMemo *me, int strand)
+{
+	if (me->epoch != st.epoch || me->cover == -1 || me->strand != strand) return false;
+	if (me->timeStamp == st.timeStamp) return true;
+	if (me->minAbundance < st.minAbundance && me->cover == -2) return true;
+	return !st.forAbundance && me->mode == 0 && me->iter == st.iter && me->cover >= 0 && me->minAbundance > 0 &&
+	       st.minAbundance > me->minAbundance && me->beta > st.minAbundance;
 }
 
 // frame layout (ints): 0 type, 1 state, 2 a, 3 b, 4 c, 5 d, 6 e, 7 f, 8 g, 9 h
@@ -228,14 +258,19 @@ PSC_DEV long long dp_memo_index(const DpState &st, const int *visit, int vcnt)
 
 // One call of SolveSubTranscript(visit = {start}, strand 0) with everything below it.  The result
 // (cover + path) is left in the memo entry whose index is returned.
-PSC_DEVN long long dp_solve_root(DpState &st, int start)
+PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 {
-	const Coop &co = st.co;
-	const CompView &v = st.v;
-	DpScratch &d = st.d;
-	int W = st.W;
+	// Work on a private copy: the caller's object has its address taken, so every store through a
+	// pointer would force the compiler to reload its fields; a local whose address never escapes
+	// lives in registers.
+	DpState st = stRef;
+	const Coop co = st.co;
+	const CompView v = st.v;
+	const DpScratch d = st.d;
+	const int W = st.W;
 	int sp = 0, extTop = 0, dpTop = 0;
 	long long ret = -1;
+	++st.nRoots;
 	uint64_t subl[2];
 	uint64_t *sub = W <= 2 ? subl : d.work + 2 * W; // the reference's attr.bufferTxpt
 	// push root
@@ -261,8 +296,7 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				dp_build_sub(st, sub, nullptr, visit, vcnt, nullptr, 0);
 				// ---- memo probe (.cpp:652-706) ----
 				bool hit = false;
-				if (me->epoch == st.epoch && me->cover != -1 && me->strand == strand &&
-				    (me->timeStamp == st.timeStamp || (me->minAbundance < st.minAbundance && me->cover == -2))) {
+				if (dp_memo_hit(st, me, strand)) {
 					if (vcnt <= 2) hit = true;
 					else if (me->cnt == vcnt && me->first == visit[0]) {
 						// the stored path restricted to [visit[0], visit[vcnt-1]] must be exactly this key
@@ -291,10 +325,10 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				int slot = dpTop++;
 				uint64_t *vb = d.fdbits + (long long)slot * W;
 				int last = visit[vcnt - 1];
-				double cover = -1;
+				double cover = -1, beta0 = 1e300;
 				if (st.ce[last]) {
 					bool bm = false;
-					cover = dp_scan_cover(st, sub, visit[0], last, tcStart, last, 0, bm);
+					cover = dp_scan_cover(st, sub, visit[0], last, tcStart, last, 0, bm, beta0);
 				}
 				// extensions: constraints whose head matches the tail of the partial path
 				int extBase = extTop, extCnt = 0;
@@ -345,6 +379,7 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				if (co.lane == 0) {
 					for (int w = 0; w < W; ++w) vb[w] = sub[w];
 					d.fdcover[slot] = cover;
+					d.fdbeta[slot] = beta0;
 					d.fdmeta[slot * 4 + 0] = visit[0];
 					d.fdmeta[slot * 4 + 1] = last;
 					d.fdmeta[slot * 4 + 2] = strand;
@@ -392,6 +427,9 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 					me->last = d.fdmeta[slot * 4 + 1];
 					me->strand = d.fdmeta[slot * 4 + 2];
 					me->cover = d.fdcover[slot];
+					me->beta = d.fdbeta[slot];
+					me->iter = st.iter;
+					me->mode = st.forAbundance ? 1 : 0;
 					me->cnt = vcnt;
 					me->minAbundance = st.minAbundance;
 					me->timeStamp = st.timeStamp;
@@ -411,62 +449,87 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 		const int *parents = d.P + ovbase;
 		int *visit = d.P + ovbase + pcnt;
 		uint64_t *pb = d.fdbits + (long long)oslot * W; // pdp.seVector
-		if (state == 0) {
-			int vcnt = FR(fi, 5) + 1;
-			int extCnt = FR(fi, 6);
-			// uncovered edges on the walk so far (kept per frame instead of rescanning the path)
-			int walkUncov = vcnt == 1 ? d.fdmeta[oslot * 4 + 3] : FR(fi - 1, 9);
-			if (dp_edge_uncovered(st, vcnt == 1 ? parents[pcnt - 1] : visit[vcnt - 2], tag)) ++walkUncov;
-			co.sync();
-			if (co.lane == 0) visit[vcnt - 1] = tag;
-			co.sync();
-			dp_build_sub(st, sub, nullptr, parents, pcnt, visit, vcnt);
-			// drop the pending extensions that no longer fit (.cpp:407-412)
-			{
-				const int *ext = d.ext + FR(owner, 6);
-				int i;
-				for (i = extCnt - 1; i >= 0; --i) {
-					int x = ext[i];
-					if (d.tcl[x] <= tag ||
-					    (bt_test(d.tcb + (long long)x * W, tag) &&
-					     compat(sub, parents[0], tag, true, d.tcb + (long long)x * W, d.tcf[x], d.tcl[x], W) != 0))
-						break;
-				}
-				extCnt = i + 1;
-			}
-			bool solveHere = v.noff[tag + 1] > v.noff[tag] &&
-			                 (extCnt == 0 || tag >= d.tcl[d.ext[FR(owner, 6) + extCnt - 1]]);
-			co.sync();
-			if (co.lane == 0) {
-				FR(fi, 5) = vcnt;
-				FR(fi, 6) = extCnt;
-				FR(fi, 8) = solveHere ? 0 : 1; // keepSearch
-				FR(fi, 9) = walkUncov;
-				FR(fi, 1) = 1;
-			}
-			if (solveHere) {
-				// the sub-problem is keyed by the walk since the owner's key: it already sits in P
-				if (co.lane == 0) {
-					FR(sp, 0) = 0; FR(sp, 1) = 0; FR(sp, 2) = ovbase + pcnt; FR(sp, 3) = vcnt; FR(sp, 4) = strand;
-					FR(sp, 5) = tcStart;
-				}
-				++sp;
-				ret = -1;
+		if (state <= 1) {
+			int vcnt, extCnt, walkUncov;
+			bool keepSearch;
+			if (state == 0) {
+				++st.nFrames;
+				vcnt = FR(fi, 5) + 1;
+				extCnt = FR(fi, 6);
+				// uncovered edges on the walk so far (kept per frame instead of rescanning the path)
+				walkUncov = vcnt == 1 ? d.fdmeta[oslot * 4 + 3] : FR(fi - 1, 9);
+				if (dp_edge_uncovered(st, vcnt == 1 ? parents[pcnt - 1] : visit[vcnt - 2], tag)) ++walkUncov;
 				co.sync();
-				continue;
+				if (co.lane == 0) visit[vcnt - 1] = tag;
+				co.sync();
+				dp_build_sub(st, sub, nullptr, parents, pcnt, visit, vcnt);
+				// drop the pending extensions that no longer fit (.cpp:407-412)
+				{
+					const int *ext = d.ext + FR(owner, 6);
+					int i;
+					for (i = extCnt - 1; i >= 0; --i) {
+						int x = ext[i];
+						if (d.tcl[x] <= tag ||
+						    (bt_test(d.tcb + (long long)x * W, tag) &&
+						     compat(sub, parents[0], tag, true, d.tcb + (long long)x * W, d.tcf[x], d.tcl[x], W) != 0))
+							break;
+					}
+					extCnt = i + 1;
+				}
+				bool solveHere = v.noff[tag + 1] > v.noff[tag] &&
+				                 (extCnt == 0 || tag >= d.tcl[d.ext[FR(owner, 6) + extCnt - 1]]);
+				keepSearch = !solveHere;
+				ret = -1;
+				if (solveHere) {
+					// The sub-problem is keyed by the walk since the owner's key; it already sits in P.
+					// Probe the memo right here: most visits are hits and then no frame is ever written.
+					long long mi = dp_memo_index(st, visit, vcnt);
+					const DpMemo *me = d.ent + mi;
+					bool hit = false;
+					if (dp_memo_hit(st, me, strand)) {
+						if (vcnt <= 2) hit = true;
+						else if (me->cnt == vcnt && me->first == visit[0]) {
+							uint64_t kl[2];
+							uint64_t *kb = W <= 2 ? kl : d.work + 3 * W;
+							dp_build_sub(st, kb, nullptr, visit, vcnt, nullptr, 0);
+							const uint64_t *mbits = d.ebits + mi * W;
+							bool same = true;
+							int lo = visit[0], hi = visit[vcnt - 1];
+							for (int w = lo >> 6; w <= (hi >> 6) && same; ++w)
+								if ((mbits[w] & keep_mask(w, lo, hi)) != kb[w]) same = false;
+							hit = same;
+						}
+					}
+					if (hit)
+						ret = mi;
+					else {
+						co.sync();
+						if (co.lane == 0) {
+							FR(fi, 5) = vcnt;
+							FR(fi, 6) = extCnt;
+							FR(fi, 8) = 0; // keepSearch
+							FR(fi, 9) = walkUncov;
+							FR(fi, 1) = 1;
+							FR(sp, 0) = 0; FR(sp, 1) = 0; FR(sp, 2) = ovbase + pcnt; FR(sp, 3) = vcnt; FR(sp, 4) = strand;
+							FR(sp, 5) = tcStart;
+						}
+						++sp;
+						co.sync();
+						continue;
+					}
+				}
+			} else {
+				vcnt = FR(fi, 5);
+				extCnt = FR(fi, 6);
+				walkUncov = FR(fi, 9);
+				keepSearch = false; // state 1 is only entered when a pushed sub-problem returns
 			}
-			ret = -1;
-			co.sync();
-			state = 1; // fall through with no sub-solution
-		}
-		if (state == 1) {
-			int vcnt = FR(fi, 5);
-			bool keepSearch = FR(fi, 8) != 0;
-			double vcover = -1;
+			double vcover = -1, vbeta = 1e300;
 			const uint64_t *vbits = nullptr;
 			int vlast = -1;
 			if (!keepSearch && ret >= 0) {
 				vcover = d.ent[ret].cover;
+				vbeta = d.ent[ret].beta;
 				vbits = d.ebits + ret * W;
 				vlast = d.ent[ret].last;
 			}
@@ -475,15 +538,17 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 			if (vcover >= 0) {
 				double cover = vcover;
 				dp_build_sub(st, sub, vbits, parents, pcnt, nullptr, 0);
-				if (!st.forAbundance && st.minAbundance > 0 && FR(fi, 9) > 0) belowMin = true;
+				if (!st.forAbundance && st.minAbundance > 0 && walkUncov > 0) belowMin = true;
 				bool bm2 = false;
-				cover = dp_scan_cover(st, sub, parents[0], vlast, tcStart, parents[pcnt - 1], cover, bm2);
+				double cbeta = vbeta;
+				cover = dp_scan_cover(st, sub, parents[0], vlast, tcStart, parents[pcnt - 1], cover, bm2, cbeta);
 				if (bm2) belowMin = true;
 				bool takeBelow = belowMin && pcover == -1;
 				if (takeBelow || (!(belowMin && pcover == -1) && cover > pcover)) {
 					co.sync();
 					if (co.lane == 0) {
 						d.fdcover[oslot] = takeBelow ? -2 : cover;
+						d.fdbeta[oslot] = cbeta;
 						for (int w = 0; w < W; ++w) pb[w] = sub[w];
 						d.fdmeta[oslot * 4 + 0] = parents[0];
 						d.fdmeta[oslot * 4 + 1] = vlast;
@@ -511,17 +576,19 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 				dp_build_sub(st, sub, nullptr, parents, pcnt, visit, vcnt);
 				double cover = 0;
 				if (st.forAbundance || st.minAbundance > 0) {
-					if (FR(fi, 9) > 0) below = true;
+					if (walkUncov > 0) below = true;
 					if (st.forAbundance && below) cover = 1e-6;
 				}
 				bool bm2 = false;
-				cover = dp_scan_cover(st, sub, parents[0], visit[vcnt - 1], tcStart, visit[vcnt - 1], cover, bm2);
+				double cbeta = 1e300;
+				cover = dp_scan_cover(st, sub, parents[0], visit[vcnt - 1], tcStart, visit[vcnt - 1], cover, bm2, cbeta);
 				if (bm2) below = true;
 				bool takeBelow = below && pcover == -1;
 				if (takeBelow || (!(below && pcover == -1) && cover > pcover)) {
 					co.sync();
 					if (co.lane == 0) {
 						d.fdcover[oslot] = takeBelow ? -2 : cover;
+						d.fdbeta[oslot] = cbeta;
 						for (int w = 0; w < W; ++w) pb[w] = sub[w];
 						d.fdmeta[oslot * 4 + 0] = parents[0];
 						d.fdmeta[oslot * 4 + 1] = visit[vcnt - 1];
@@ -537,6 +604,10 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 			}
 			co.sync();
 			if (co.lane == 0) {
+				FR(fi, 5) = vcnt;
+				FR(fi, 6) = extCnt;
+				FR(fi, 8) = 1;
+				FR(fi, 9) = walkUncov;
 				FR(fi, 1) = 2;
 				FR(fi, 7) = v.noff[tag];
 			}
@@ -571,6 +642,9 @@ PSC_DEVN long long dp_solve_root(DpState &st, int start)
 		}
 	}
 	co.sync();
+	stRef.nStates = st.nStates;
+	stRef.nFrames = st.nFrames;
+	stRef.nRoots = st.nRoots;
 	return ret;
 }
 #undef FR
@@ -601,6 +675,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 	DpScratch &d = st.d;
 	int W = st.W, n = v.n, tcCnt = d.tcCnt;
 	st.timeStamp = 1;
+	st.iter = 0;
 	++st.epoch;
 	// tcEnd[q] = number of constraints starting at or before subexon q (they are sorted by .first)
 	for (int q = co.lane; q < n; q += co.n) {
@@ -640,7 +715,9 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 	st.minAbundance = 0;
 	for (int i = 0; i < n; ++i)
 		if (st.cs[i]) {
+			long long tq = clock64();
 			long long r = dp_solve_root(st, i);
+			st.cycRoot += clock64() - tq;
 			double c = d.ent[r].cover;
 			if (c > maxAbundance) maxAbundance = c;
 		}
@@ -655,6 +732,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 	for (;;) {
 		double bestScore = -1;
 		st.minAbundance = 0;
+		++st.iter; // constraint abundances change between iterations: memo entries do not carry over
 		best.cover = -1;
 		for (;;) {
 			// cached result for this minAbundance? (.cpp:996-1000)
@@ -669,7 +747,9 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 				++st.nLevels;
 				for (int i = 0; i < n; ++i) {
 					if (!st.cs[i]) continue;
+					long long tq = clock64();
 					long long r = dp_solve_root(st, i);
+					st.cycRoot += clock64() - tq;
 					double c = d.ent[r].cover;
 					if (c > maxCover.cover && c > 0) dp_take(st, maxCover, d.ebits + r * W, c, d.ent[r].first, d.ent[r].last);
 				}
@@ -722,6 +802,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 		}
 		if (best.cover == -1) break;
 		// ---- assign the constraints of the best path (.cpp:1074-1152) ----
+		long long tqa = clock64();
 		int coveredCnt = 0;
 		double update = 1e300;
 		int anyu = 0;
@@ -768,6 +849,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 			if (co.lane == 0) d.tcab[j] = ab;
 			co.sync();
 		}
+		st.cycAssign += clock64() - tqa;
 		++iterCnt;
 		++st.nIters;
 		if (iterCnt >= iterBound) break;
@@ -929,6 +1011,7 @@ PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
 	int *P = cv.take<int>((size_t)n + 4);
 	int *fr = cv.take<int>((size_t)(2 * n + 6) * PSC_FR_INTS);
 	double *fdcover = cv.take<double>((size_t)n + 3);
+	double *fdbeta = cv.take<double>((size_t)n + 3);
 	int *fdmeta = cv.take<int>((size_t)(n + 3) * 4);
 	uint64_t *fdbits = cv.take<uint64_t>((size_t)(n + 3) * W);
 	uint64_t *work = cv.take<uint64_t>((size_t)8 * W);
@@ -936,6 +1019,7 @@ PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
 	d.P = P;
 	d.fr = fr;
 	d.fdcover = fdcover;
+	d.fdbeta = fdbeta;
 	d.fdmeta = fdmeta;
 	d.fdbits = fdbits;
 	d.work = work;
@@ -945,7 +1029,7 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
                            char *txBase, int *n_tx_out, char *sm, size_t smBytes, long long *dbg)
 {
 	DpState st;
-	st.nStates = st.nLevels = st.nIters = 0;
+	st.nStates = st.nLevels = st.nIters = st.nFrames = st.nRoots = st.cycRoot = st.cycAssign = 0;
 	long long t0 = clock64();
 	st.co = co;
 	st.v = comp_view(g, u.comp);
@@ -1008,9 +1092,9 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 	if (co.lane == 0) *n_tx_out = nt;
 	if (dbg && co.lane == 0) {
 		dbg[0] = clock64() - t0;
-		dbg[1] = st.nStates;
-		dbg[2] = st.nLevels;
-		dbg[3] = st.nIters;
+		dbg[1] = st.nStates + ((st.cycRoot >> 20) << 32);
+		dbg[2] = st.nLevels + ((st.cycAssign >> 20) << 32);
+		dbg[3] = st.nIters + (st.nFrames << 12) + (st.nRoots << 40);
 	}
 	co.sync();
 }

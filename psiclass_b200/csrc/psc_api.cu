@@ -203,6 +203,7 @@ int psc_create(psc_ctx **out, int device)
 	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return 2; // no CUDA device: there is no CPU fallback
 	if (device < 0 || device >= n) return 3;
 	if (cudaSetDevice(device) != cudaSuccess) return 4;
+	cudaDeviceSetLimit(cudaLimitStackSize, 4096); // the DP state machine keeps a private copy of its state on the stack
 	psc_ctx *ctx = new psc_ctx;
 	ctx->device = device;
 	cudaDeviceProp prop;

@@ -359,15 +359,20 @@ int psc_solve(psc_ctx *ctx)
 				std::vector<int> ix((size_t)nUnits);
 				for (int u = 0; u < nUnits; ++u) ix[(size_t)u] = u;
 				std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 4] > h[(size_t)b * 4]; });
-				long long tot = 0;
-				for (int u = 0; u < nUnits; ++u) tot += h[(size_t)u * 4];
-				fprintf(stderr, "[dp] %d units, total %.1f Mcycles\n", nUnits, tot / 1e6);
+				long long tot = 0, totStates = 0, totFrames = 0;
+				for (int u = 0; u < nUnits; ++u) {
+					tot += h[(size_t)u * 4];
+					totStates += h[(size_t)u * 4 + 1] & 0xffffffff;
+					totFrames += (h[(size_t)u * 4 + 3] >> 12) & 0xfffffff;
+				}
+				fprintf(stderr, "[dp] %d units, total %.1f Mcycles, %lld states, %lld frames\n", nUnits, tot / 1e6, totStates, totFrames);
 				for (int k = 0; k < 12 && k < nUnits; ++k) {
 					int u = ix[(size_t)k];
 					int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
-					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld\n", u, c, s,
+					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld\n", u, c, s,
 					        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
-					        h[(size_t)u * 4] / 1e6, h[(size_t)u * 4 + 1], h[(size_t)u * 4 + 2], h[(size_t)u * 4 + 3]);
+					        h[(size_t)u * 4] / 1e6, h[(size_t)u * 4 + 1] & 0xffffffff, h[(size_t)u * 4 + 2] & 0xffffffff, h[(size_t)u * 4 + 3] & 0xfff, (h[(size_t)u * 4 + 3] >> 12) & 0xfffffff, h[(size_t)u * 4 + 3] >> 40,
+					        h[(size_t)u * 4 + 1] >> 32, h[(size_t)u * 4 + 2] >> 32);
 				}
 			}
 			i0 = i1;

@@ -55,6 +55,8 @@ struct cudaDeviceProp { int multiProcessorCount; size_t totalGlobalMem; char nam
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->multiProcessorCount = 1; p->totalGlobalMem = (size_t)8 << 30; strcpy(p->name, "cpu-shim"); return 0; }
 static inline cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = (size_t)8 << 30; *t = (size_t)8 << 30; return 0; }
 
+enum cudaLimit { cudaLimitStackSize };
+static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return 0; }
 static inline long long clock64() { return 0; }
 
 // serial kernel launch: one "block" of one "thread"
