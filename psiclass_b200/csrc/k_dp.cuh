@@ -128,7 +128,7 @@ struct DpState {
 	double minAbundance;
 	int timeStamp, epoch, iter;
 	int *err;
-	long long nStates, nLevels, nIters, nFrames, nRoots, cycRoot, cycAssign; // instrumentation (PSC_DEBUG_DP)
+	mutable long long nStates, nLevels, nIters, nFrames, nRoots, cycRoot, cycAssign, sumExt, sumDrop, sumScan; // instrumentation (PSC_DEBUG_DP)
 };
 
 PSC_DEV bool dp_edge_uncovered(const DpState &st, int a, int b)
@@ -181,6 +181,7 @@ PSC_DEV double dp_scan_cover(const DpState &st, const uint64_t *tb, int tf, int 
 {
 	int end = dp_tc_end(st, tcStart, bound);
 	if (end <= tcStart) return cover; // nothing starts inside the range: no lane has work, no reduction
+	st.sumScan += end - tcStart;
 	bool below = false;
 	int cnt = 0, ccnt = 0;
 	double mn = 1e300, mnAll = 1e300;
@@ -355,13 +356,37 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 					if (extCnt > 1) {
 						int *src = d.ext + extBase, *tmp = src + extCnt;
 						if (extBase + 2 * extCnt <= d.extCap) {
+							// keys are subexon indices just past the key's end (constraints are truncated to a few
+							// subexons): a stable counting sort over the few distinct values, one ballot per
+							// (value, 32 elements)
+							int kmin = 0x7fffffff, kmax = -1;
 							for (int a = co.lane; a < extCnt; a += co.n) {
-								int x = src[a], xl = d.tcl[x], r = 0;
-								for (int b = 0; b < extCnt; ++b) {
-									int yl = d.tcl[src[b]];
-									if (yl < xl || (yl == xl && b < a)) ++r;
+								int k = d.tcl[src[a]];
+								if (k < kmin) kmin = k;
+								if (k > kmax) kmax = k;
+							}
+							kmin = co.min(kmin);
+							kmax = co.max(kmax);
+							if (kmax - kmin < 24) {
+								int base = 0;
+								for (int kv = kmin; kv <= kmax; ++kv)
+									for (int b0 = 0; b0 < extCnt; b0 += co.n) {
+										int a = b0 + co.lane;
+										int x = a < extCnt ? src[a] : -1;
+										bool is = a < extCnt && d.tcl[x] == kv;
+										uint32_t m = co.ballot(is);
+										if (is) tmp[base + co.rank_in(m)] = x;
+										base += popc32(m);
+									}
+							} else {
+								for (int a = co.lane; a < extCnt; a += co.n) {
+									int x = src[a], xl = d.tcl[x], r = 0;
+									for (int b = 0; b < extCnt; ++b) {
+										int yl = d.tcl[src[b]];
+										if (yl < xl || (yl == xl && b < a)) ++r;
+									}
+									tmp[r] = x;
 								}
-								tmp[r] = x;
 							}
 							co.sync();
 							for (int a = co.lane; a < extCnt; a += co.n) src[a] = tmp[a];
@@ -376,6 +401,7 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 					}
 				}
 				extTop = extBase + extCnt;
+				st.sumExt += extCnt;
 				if (co.lane == 0) {
 					for (int w = 0; w < W; ++w) vb[w] = sub[w];
 					d.fdcover[slot] = cover;
@@ -468,6 +494,7 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 					const int *ext = d.ext + FR(owner, 6);
 					int i;
 					for (i = extCnt - 1; i >= 0; --i) {
+						++st.sumDrop;
 						int x = ext[i];
 						if (d.tcl[x] <= tag ||
 						    (bt_test(d.tcb + (long long)x * W, tag) &&
@@ -643,6 +670,9 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 	}
 	co.sync();
 	stRef.nStates = st.nStates;
+	stRef.sumExt = st.sumExt;
+	stRef.sumDrop = st.sumDrop;
+	stRef.sumScan = st.sumScan;
 	stRef.nFrames = st.nFrames;
 	stRef.nRoots = st.nRoots;
 	return ret;
@@ -1029,7 +1059,7 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
                            char *txBase, int *n_tx_out, char *sm, size_t smBytes, long long *dbg)
 {
 	DpState st;
-	st.nStates = st.nLevels = st.nIters = st.nFrames = st.nRoots = st.cycRoot = st.cycAssign = 0;
+	st.nStates = st.nLevels = st.nIters = st.nFrames = st.nRoots = st.cycRoot = st.cycAssign = st.sumExt = st.sumDrop = st.sumScan = 0;
 	long long t0 = clock64();
 	st.co = co;
 	st.v = comp_view(g, u.comp);
@@ -1092,6 +1122,9 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 	if (co.lane == 0) *n_tx_out = nt;
 	if (dbg && co.lane == 0) {
 		dbg[0] = clock64() - t0;
+		dbg[4] = st.sumExt;
+		dbg[5] = st.sumDrop;
+		dbg[6] = st.sumScan;
 		dbg[1] = st.nStates + ((st.cycRoot >> 20) << 32);
 		dbg[2] = st.nLevels + ((st.cycAssign >> 20) << 32);
 		dbg[3] = st.nIters + (st.nFrames << 12) + (st.nRoots << 40);

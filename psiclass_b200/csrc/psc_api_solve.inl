@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) k_dp_units(GraphDev g, SolveDev sv, const
 		u = co.bcast(u, 0);
 		if (u >= nUnits) break;
 		int ui = order[u];
-		dp_unit_pick(co, g, sv, units[ui], scratch, txArena, n_tx + ui, sm, smBytes, dbg ? dbg + 4 * (long long)ui : nullptr);
+		dp_unit_pick(co, g, sv, units[ui], scratch, txArena, n_tx + ui, sm, smBytes, dbg ? dbg + 8 * (long long)ui : nullptr);
 		co.sync();
 	}
 }
@@ -329,8 +329,8 @@ int psc_solve(psc_ctx *ctx)
 				long long *dbgPtr = nullptr;
 				const bool dbgOn = getenv("PSC_DEBUG_DP") != nullptr;
 				if (dbgOn) {
-					if (!st.dp_dbg.ensure(sizeof(long long) * 4 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
-					CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 4 * (size_t)(nUnits + 1), ctx->stream));
+					if (!st.dp_dbg.ensure(sizeof(long long) * 8 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
+					CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 8 * (size_t)(nUnits + 1), ctx->stream));
 					dbgPtr = st.dp_dbg.as<long long>();
 				}
 #ifndef PSC_CPU_SHIM
@@ -354,25 +354,25 @@ int psc_solve(psc_ctx *ctx)
 			CK(cudaGetLastError());
 			CK(cudaStreamSynchronize(ctx->stream));
 			if (getenv("PSC_DEBUG_DP")) {
-				std::vector<long long> h((size_t)nUnits * 4);
+				std::vector<long long> h((size_t)nUnits * 8);
 				cudaMemcpy(h.data(), st.dp_dbg.p, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
 				std::vector<int> ix((size_t)nUnits);
 				for (int u = 0; u < nUnits; ++u) ix[(size_t)u] = u;
-				std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 4] > h[(size_t)b * 4]; });
+				std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 8] > h[(size_t)b * 8]; });
 				long long tot = 0, totStates = 0, totFrames = 0;
 				for (int u = 0; u < nUnits; ++u) {
-					tot += h[(size_t)u * 4];
-					totStates += h[(size_t)u * 4 + 1] & 0xffffffff;
-					totFrames += (h[(size_t)u * 4 + 3] >> 12) & 0xfffffff;
+					tot += h[(size_t)u * 8];
+					totStates += h[(size_t)u * 8 + 1] & 0xffffffff;
+					totFrames += (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff;
 				}
 				fprintf(stderr, "[dp] %d units, total %.1f Mcycles, %lld states, %lld frames\n", nUnits, tot / 1e6, totStates, totFrames);
 				for (int k = 0; k < 12 && k < nUnits; ++k) {
 					int u = ix[(size_t)k];
 					int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
-					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld\n", u, c, s,
+					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld | ext %lld drop %lld scan %lld\n", u, c, s,
 					        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
-					        h[(size_t)u * 4] / 1e6, h[(size_t)u * 4 + 1] & 0xffffffff, h[(size_t)u * 4 + 2] & 0xffffffff, h[(size_t)u * 4 + 3] & 0xfff, (h[(size_t)u * 4 + 3] >> 12) & 0xfffffff, h[(size_t)u * 4 + 3] >> 40,
-					        h[(size_t)u * 4 + 1] >> 32, h[(size_t)u * 4 + 2] >> 32);
+					        h[(size_t)u * 8] / 1e6, h[(size_t)u * 8 + 1] & 0xffffffff, h[(size_t)u * 8 + 2] & 0xffffffff, h[(size_t)u * 8 + 3] & 0xfff, (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff, h[(size_t)u * 8 + 3] >> 40,
+					        h[(size_t)u * 8 + 1] >> 32, h[(size_t)u * 8 + 2] >> 32, h[(size_t)u * 8 + 4], h[(size_t)u * 8 + 5], h[(size_t)u * 8 + 6]);
 				}
 			}
 			i0 = i1;
