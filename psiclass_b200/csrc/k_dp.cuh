@@ -35,6 +35,8 @@ struct DpScratch {
 	int *P;         // the path stack: solve keys and search extensions share it
 	int *fr;        // frames
 	double *fdcover, *fdbeta;
+	uint64_t *fdkey; // [(n+3)*W] key bits per owner
+	uint64_t *pbits; // [(n+4)*W] owner key | walk, per path position
 	int *fdmeta; // first,last,strand,#uncovered edges inside the key: per solve frame
 	int *tcEnd;  // [n+1] number of constraints whose .first <= q
 	uint64_t *fdbits;
@@ -86,6 +88,8 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 	s.fdmeta = cv.take<int>((size_t)(n + 3) * 4);
 	s.tcEnd = cv.take<int>((size_t)n + 2);
 	s.fdbits = cv.take<uint64_t>((size_t)(n + 3) * W);
+	s.fdkey = cv.take<uint64_t>((size_t)(n + 3) * W);
+	s.pbits = cv.take<uint64_t>((size_t)(n + 4) * W);
 	long long ec = (long long)(n + 2) * (Cmax + 1);
 	if (ec > (long long)4 << 20) ec = (long long)4 << 20;
 	s.extCap = (int)ec;
@@ -181,7 +185,6 @@ PSC_DEV double dp_scan_cover(const DpState &st, const uint64_t *tb, int tf, int 
 {
 	int end = dp_tc_end(st, tcStart, bound);
 	if (end <= tcStart) return cover; // nothing starts inside the range: no lane has work, no reduction
-	st.sumScan += end - tcStart;
 	bool below = false;
 	int cnt = 0, ccnt = 0;
 	double mn = 1e300, mnAll = 1e300;
@@ -252,432 +255,64 @@ PSC_DEV bool dp_memo_hit(const DpState &st, const DpMemo *me, int strand)
 	       st.minAbundance > me->minAbundance && me->beta > st.minAbundance;
 }
 
-// frame layout (ints): 0 type, 1 state, 2 a, 3 b, 4 c, 5 d, 6 e, 7 f, 8 g, 9 h
-//  solve : a=vbase b=vcnt c=strand d=tcStart e=extBase f=extCnt g=edge iterator h=dp slot
-//  search: a=tag  b=strand c=owner frame d=vcnt(after) e=extCnt f=edge iterator g=keepSearch
-#define FR(i, k) st.d.fr[(i) * PSC_FR_INTS + (k)]
-
-// One call of SolveSubTranscript(visit = {start}, strand 0) with everything below it.  The result
-// (cover + path) is left in the memo entry whose index is returned.
-PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
+// stable sort of an extension list by .last (.cpp:781-796; glibc qsort == merge sort).  The keys are
+// subexon indices just past the key's end (constraints are truncated to a few subexons): a stable
+// counting sort over the few distinct values, one ballot per (value, 32 elements); wide key ranges fall
+// back to ranking every element against all others.
+PSC_DEV void dp_sort_ext(const DpState &st, int *src, int extCnt, bool hasRoom)
 {
-	// Work on a private copy: the caller's object has its address taken, so every store through a
-	// pointer would force the compiler to reload its fields; a local whose address never escapes
-	// lives in registers.
-	DpState st = stRef;
-	const Coop co = st.co;
-	const CompView v = st.v;
-	const DpScratch d = st.d;
-	const int W = st.W;
-	int sp = 0, extTop = 0, dpTop = 0;
-	long long ret = -1;
-	++st.nRoots;
-	uint64_t subl[2];
-	uint64_t *sub = W <= 2 ? subl : d.work + 2 * W; // the reference's attr.bufferTxpt
-	// push root
-	co.sync();
-	if (co.lane == 0) {
-		d.P[0] = start;
-		FR(0, 0) = 0; FR(0, 1) = 0; FR(0, 2) = 0; FR(0, 3) = 1; FR(0, 4) = 0; FR(0, 5) = 0;
+	const Coop &co = st.co;
+	const DpScratch &d = st.d;
+	if (extCnt <= 1) return;
+	int *tmp = src + extCnt;
+	if (hasRoom) {
+		int kmin = 0x7fffffff, kmax = -1;
+		for (int a = co.lane; a < extCnt; a += co.n) {
+			int k = d.tcl[src[a]];
+			if (k < kmin) kmin = k;
+			if (k > kmax) kmax = k;
+		}
+		kmin = co.min(kmin);
+		kmax = co.max(kmax);
+		if (kmax - kmin < 24) {
+			int base = 0;
+			for (int kv = kmin; kv <= kmax; ++kv)
+				for (int b0 = 0; b0 < extCnt; b0 += co.n) {
+					int a = b0 + co.lane;
+					int x = a < extCnt ? src[a] : -1;
+					bool is = a < extCnt && d.tcl[x] == kv;
+					uint32_t m = co.ballot(is);
+					if (is) tmp[base + co.rank_in(m)] = x;
+					base += popc32(m);
+				}
+		} else {
+			for (int a = co.lane; a < extCnt; a += co.n) {
+				int x = src[a], xl = d.tcl[x], r = 0;
+				for (int b = 0; b < extCnt; ++b) {
+					int yl = d.tcl[src[b]];
+					if (yl < xl || (yl == xl && b < a)) ++r;
+				}
+				tmp[r] = x;
+			}
+		}
+		co.sync();
+		for (int a = co.lane; a < extCnt; a += co.n) src[a] = tmp[a];
+		co.sync();
+	} else {
+		if (co.lane == 0)
+			for (int a = 1; a < extCnt; ++a) {
+				int x = src[a], xl = d.tcl[x], b = a - 1;
+				while (b >= 0 && d.tcl[src[b]] > xl) { src[b + 1] = src[b]; --b; }
+				src[b + 1] = x;
+			}
+		co.sync();
 	}
-	sp = 1;
-	co.sync();
-	while (sp > 0) {
-		int fi = sp - 1;
-		int type = FR(fi, 0), state = FR(fi, 1);
-		if (type == 0) {
-			// ================= SolveSubTranscript =================
-			int vbase = FR(fi, 2), vcnt = FR(fi, 3), strand = FR(fi, 4);
-			const int *visit = d.P + vbase;
-			long long mi = dp_memo_index(st, visit, vcnt);
-			DpMemo *me = d.ent + mi;
-			uint64_t *mbits = d.ebits + mi * W;
-			if (state == 0) {
-				// bits of the key (needed for the hash probe and, on a miss, as the start of the path)
-				dp_build_sub(st, sub, nullptr, visit, vcnt, nullptr, 0);
-				// ---- memo probe (.cpp:652-706) ----
-				bool hit = false;
-				if (dp_memo_hit(st, me, strand)) {
-					if (vcnt <= 2) hit = true;
-					else if (me->cnt == vcnt && me->first == visit[0]) {
-						// the stored path restricted to [visit[0], visit[vcnt-1]] must be exactly this key
-						bool same = true;
-						int lo = visit[0], hi = visit[vcnt - 1];
-						for (int w = lo >> 6; w <= (hi >> 6) && same; ++w)
-							if ((mbits[w] & keep_mask(w, lo, hi)) != sub[w]) same = false;
-						hit = same;
-					}
-				}
-				if (hit) {
-					ret = mi;
-					--sp;
-					continue;
-				}
-				// ---- fresh evaluation ----
-				++st.nStates;
-				int tcStart = FR(fi, 5);
-				{ // first constraint with first >= visit[0]
-					int lo = visit[0] > 0 ? d.tcEnd[visit[0] - 1] : 0;
-					if (lo > tcStart) tcStart = lo;
-				}
-				int keyUncov = 0;
-				for (int i = 0; i + 1 < vcnt; ++i)
-					if (dp_edge_uncovered(st, visit[i], visit[i + 1])) ++keyUncov;
-				int slot = dpTop++;
-				uint64_t *vb = d.fdbits + (long long)slot * W;
-				int last = visit[vcnt - 1];
-				double cover = -1, beta0 = 1e300;
-				if (st.ce[last]) {
-					bool bm = false;
-					cover = dp_scan_cover(st, sub, visit[0], last, tcStart, last, 0, bm, beta0);
-				}
-				// extensions: constraints whose head matches the tail of the partial path
-				int extBase = extTop, extCnt = 0;
-				{
-					int end = dp_tc_end(st, tcStart, last);
-					for (int b0 = tcStart; b0 < end; b0 += co.n) {
-						int i = b0 + co.lane;
-						bool is = i < end && compat(sub, visit[0], last, true, d.tcb + (long long)i * W, d.tcf[i], d.tcl[i], W) == 2;
-						uint32_t m = co.ballot(is);
-						if (is) {
-							int p = extBase + extCnt + co.rank_in(m);
-							if (p < d.extCap) d.ext[p] = i;
-						}
-						extCnt += popc32(m);
-					}
-					if (extBase + extCnt > d.extCap) {
-						*st.err = 21;
-						extCnt = d.extCap - extBase;
-					}
-					co.sync();
-					// stable sort by .last (.cpp:781-796; glibc qsort == merge sort): every lane ranks its
-					// elements (count of smaller keys, ties by position) and scatters them into the free space
-					// above the list, which is then copied back
-					if (extCnt > 1) {
-						int *src = d.ext + extBase, *tmp = src + extCnt;
-						if (extBase + 2 * extCnt <= d.extCap) {
-							// keys are subexon indices just past the key's end (constraints are truncated to a few
-							// subexons): a stable counting sort over the few distinct values, one ballot per
-							// (value, 32 elements)
-							int kmin = 0x7fffffff, kmax = -1;
-							for (int a = co.lane; a < extCnt; a += co.n) {
-								int k = d.tcl[src[a]];
-								if (k < kmin) kmin = k;
-								if (k > kmax) kmax = k;
-							}
-							kmin = co.min(kmin);
-							kmax = co.max(kmax);
-							if (kmax - kmin < 24) {
-								int base = 0;
-								for (int kv = kmin; kv <= kmax; ++kv)
-									for (int b0 = 0; b0 < extCnt; b0 += co.n) {
-										int a = b0 + co.lane;
-										int x = a < extCnt ? src[a] : -1;
-										bool is = a < extCnt && d.tcl[x] == kv;
-										uint32_t m = co.ballot(is);
-										if (is) tmp[base + co.rank_in(m)] = x;
-										base += popc32(m);
-									}
-							} else {
-								for (int a = co.lane; a < extCnt; a += co.n) {
-									int x = src[a], xl = d.tcl[x], r = 0;
-									for (int b = 0; b < extCnt; ++b) {
-										int yl = d.tcl[src[b]];
-										if (yl < xl || (yl == xl && b < a)) ++r;
-									}
-									tmp[r] = x;
-								}
-							}
-							co.sync();
-							for (int a = co.lane; a < extCnt; a += co.n) src[a] = tmp[a];
-							co.sync();
-						} else if (co.lane == 0) {
-							for (int a = 1; a < extCnt; ++a) {
-								int x = src[a], xl = d.tcl[x], b = a - 1;
-								while (b >= 0 && d.tcl[src[b]] > xl) { src[b + 1] = src[b]; --b; }
-								src[b + 1] = x;
-							}
-						}
-					}
-				}
-				extTop = extBase + extCnt;
-				st.sumExt += extCnt;
-				if (co.lane == 0) {
-					for (int w = 0; w < W; ++w) vb[w] = sub[w];
-					d.fdcover[slot] = cover;
-					d.fdbeta[slot] = beta0;
-					d.fdmeta[slot * 4 + 0] = visit[0];
-					d.fdmeta[slot * 4 + 1] = last;
-					d.fdmeta[slot * 4 + 2] = strand;
-					d.fdmeta[slot * 4 + 3] = keyUncov;
-					FR(fi, 1) = 1;
-					FR(fi, 5) = tcStart;
-					FR(fi, 6) = extBase;
-					FR(fi, 7) = extCnt;
-					FR(fi, 8) = v.noff[last];
-					FR(fi, 9) = slot;
-				}
-				co.sync();
-				continue;
-			}
-			// ---- state 1: iterate the successors of the last subexon of the key (.cpp:798-819) ----
-			{
-				int a = visit[vcnt - 1];
-				int ei = FR(fi, 8);
-				bool pushed = false;
-				while (ei < v.noff[a + 1]) {
-					int b = v.nidx[ei++];
-					if ((same_strand(v.rs[a], strand) && same_strand(v.ls[b], strand)) || v.st[b] == v.en[a] + 1) {
-						int ns = strand;
-						if (v.st[b] > v.en[a] + 1) ns = v.rs[a];
-						co.sync();
-						if (co.lane == 0) {
-							FR(fi, 8) = ei;
-							FR(sp, 0) = 1; FR(sp, 1) = 0; FR(sp, 2) = b; FR(sp, 3) = ns; FR(sp, 4) = fi; FR(sp, 5) = 0;
-							FR(sp, 6) = FR(fi, 7);
-						}
-						++sp;
-						co.sync();
-						pushed = true;
-						break;
-					}
-				}
-				if (pushed) continue;
-				// ---- done: store in the memo (.cpp:824-856) ----
-				int slot = FR(fi, 9);
-				co.sync();
-				if (co.lane == 0) {
-					const uint64_t *vb = d.fdbits + (long long)slot * W;
-					for (int w = 0; w < W; ++w) mbits[w] = vb[w];
-					me->first = d.fdmeta[slot * 4 + 0];
-					me->last = d.fdmeta[slot * 4 + 1];
-					me->strand = d.fdmeta[slot * 4 + 2];
-					me->cover = d.fdcover[slot];
-					me->beta = d.fdbeta[slot];
-					me->iter = st.iter;
-					me->mode = st.forAbundance ? 1 : 0;
-					me->cnt = vcnt;
-					me->minAbundance = st.minAbundance;
-					me->timeStamp = st.timeStamp;
-					me->epoch = st.epoch;
-				}
-				co.sync();
-				extTop = FR(fi, 6);
-				dpTop = slot;
-				ret = mi;
-				--sp;
-				continue;
-			}
-		}
-		// ================= SearchSubTranscript =================
-		int tag = FR(fi, 2), strand = FR(fi, 3), owner = FR(fi, 4);
-		int ovbase = FR(owner, 2), pcnt = FR(owner, 3), tcStart = FR(owner, 5), oslot = FR(owner, 9);
-		const int *parents = d.P + ovbase;
-		int *visit = d.P + ovbase + pcnt;
-		uint64_t *pb = d.fdbits + (long long)oslot * W; // pdp.seVector
-		if (state <= 1) {
-			int vcnt, extCnt, walkUncov;
-			bool keepSearch;
-			if (state == 0) {
-				++st.nFrames;
-				vcnt = FR(fi, 5) + 1;
-				extCnt = FR(fi, 6);
-				// uncovered edges on the walk so far (kept per frame instead of rescanning the path)
-				walkUncov = vcnt == 1 ? d.fdmeta[oslot * 4 + 3] : FR(fi - 1, 9);
-				if (dp_edge_uncovered(st, vcnt == 1 ? parents[pcnt - 1] : visit[vcnt - 2], tag)) ++walkUncov;
-				co.sync();
-				if (co.lane == 0) visit[vcnt - 1] = tag;
-				co.sync();
-				dp_build_sub(st, sub, nullptr, parents, pcnt, visit, vcnt);
-				// drop the pending extensions that no longer fit (.cpp:407-412)
-				{
-					const int *ext = d.ext + FR(owner, 6);
-					int i;
-					for (i = extCnt - 1; i >= 0; --i) {
-						++st.sumDrop;
-						int x = ext[i];
-						if (d.tcl[x] <= tag ||
-						    (bt_test(d.tcb + (long long)x * W, tag) &&
-						     compat(sub, parents[0], tag, true, d.tcb + (long long)x * W, d.tcf[x], d.tcl[x], W) != 0))
-							break;
-					}
-					extCnt = i + 1;
-				}
-				bool solveHere = v.noff[tag + 1] > v.noff[tag] &&
-				                 (extCnt == 0 || tag >= d.tcl[d.ext[FR(owner, 6) + extCnt - 1]]);
-				keepSearch = !solveHere;
-				ret = -1;
-				if (solveHere) {
-					// The sub-problem is keyed by the walk since the owner's key; it already sits in P.
-					// Probe the memo right here: most visits are hits and then no frame is ever written.
-					long long mi = dp_memo_index(st, visit, vcnt);
-					const DpMemo *me = d.ent + mi;
-					bool hit = false;
-					if (dp_memo_hit(st, me, strand)) {
-						if (vcnt <= 2) hit = true;
-						else if (me->cnt == vcnt && me->first == visit[0]) {
-							uint64_t kl[2];
-							uint64_t *kb = W <= 2 ? kl : d.work + 3 * W;
-							dp_build_sub(st, kb, nullptr, visit, vcnt, nullptr, 0);
-							const uint64_t *mbits = d.ebits + mi * W;
-							bool same = true;
-							int lo = visit[0], hi = visit[vcnt - 1];
-							for (int w = lo >> 6; w <= (hi >> 6) && same; ++w)
-								if ((mbits[w] & keep_mask(w, lo, hi)) != kb[w]) same = false;
-							hit = same;
-						}
-					}
-					if (hit)
-						ret = mi;
-					else {
-						co.sync();
-						if (co.lane == 0) {
-							FR(fi, 5) = vcnt;
-							FR(fi, 6) = extCnt;
-							FR(fi, 8) = 0; // keepSearch
-							FR(fi, 9) = walkUncov;
-							FR(fi, 1) = 1;
-							FR(sp, 0) = 0; FR(sp, 1) = 0; FR(sp, 2) = ovbase + pcnt; FR(sp, 3) = vcnt; FR(sp, 4) = strand;
-							FR(sp, 5) = tcStart;
-						}
-						++sp;
-						co.sync();
-						continue;
-					}
-				}
-			} else {
-				vcnt = FR(fi, 5);
-				extCnt = FR(fi, 6);
-				walkUncov = FR(fi, 9);
-				keepSearch = false; // state 1 is only entered when a pushed sub-problem returns
-			}
-			double vcover = -1, vbeta = 1e300;
-			const uint64_t *vbits = nullptr;
-			int vlast = -1;
-			if (!keepSearch && ret >= 0) {
-				vcover = d.ent[ret].cover;
-				vbeta = d.ent[ret].beta;
-				vbits = d.ebits + ret * W;
-				vlast = d.ent[ret].last;
-			}
-			double pcover = d.fdcover[oslot];
-			bool belowMin = false;
-			if (vcover >= 0) {
-				double cover = vcover;
-				dp_build_sub(st, sub, vbits, parents, pcnt, nullptr, 0);
-				if (!st.forAbundance && st.minAbundance > 0 && walkUncov > 0) belowMin = true;
-				bool bm2 = false;
-				double cbeta = vbeta;
-				cover = dp_scan_cover(st, sub, parents[0], vlast, tcStart, parents[pcnt - 1], cover, bm2, cbeta);
-				if (bm2) belowMin = true;
-				bool takeBelow = belowMin && pcover == -1;
-				if (takeBelow || (!(belowMin && pcover == -1) && cover > pcover)) {
-					co.sync();
-					if (co.lane == 0) {
-						d.fdcover[oslot] = takeBelow ? -2 : cover;
-						d.fdbeta[oslot] = cbeta;
-						for (int w = 0; w < W; ++w) pb[w] = sub[w];
-						d.fdmeta[oslot * 4 + 0] = parents[0];
-						d.fdmeta[oslot * 4 + 1] = vlast;
-						d.fdmeta[oslot * 4 + 2] = strand;
-					}
-					co.sync();
-					pcover = takeBelow ? -2 : cover;
-				}
-			} else if (vcover == -2 && pcover == -1) {
-				co.sync();
-				if (co.lane == 0) {
-					for (int w = 0; w < W; ++w) pb[w] = vbits[w];
-					for (int i = 0; i < pcnt; ++i) bt_set(pb, parents[i]);
-					d.fdcover[oslot] = -2;
-					d.fdmeta[oslot * 4 + 0] = parents[0];
-					d.fdmeta[oslot * 4 + 1] = vlast;
-					d.fdmeta[oslot * 4 + 2] = strand;
-				}
-				co.sync();
-				pcover = -2;
-			}
-			// the path may also stop at this subexon (.cpp:524-614)
-			if (st.ce[tag] && (vcover < 0 || st.forAbundance)) {
-				bool below = false;
-				dp_build_sub(st, sub, nullptr, parents, pcnt, visit, vcnt);
-				double cover = 0;
-				if (st.forAbundance || st.minAbundance > 0) {
-					if (walkUncov > 0) below = true;
-					if (st.forAbundance && below) cover = 1e-6;
-				}
-				bool bm2 = false;
-				double cbeta = 1e300;
-				cover = dp_scan_cover(st, sub, parents[0], visit[vcnt - 1], tcStart, visit[vcnt - 1], cover, bm2, cbeta);
-				if (bm2) below = true;
-				bool takeBelow = below && pcover == -1;
-				if (takeBelow || (!(below && pcover == -1) && cover > pcover)) {
-					co.sync();
-					if (co.lane == 0) {
-						d.fdcover[oslot] = takeBelow ? -2 : cover;
-						d.fdbeta[oslot] = cbeta;
-						for (int w = 0; w < W; ++w) pb[w] = sub[w];
-						d.fdmeta[oslot * 4 + 0] = parents[0];
-						d.fdmeta[oslot * 4 + 1] = visit[vcnt - 1];
-						d.fdmeta[oslot * 4 + 2] = strand;
-					}
-					co.sync();
-				}
-			}
-			if (!keepSearch) {
-				--sp;
-				ret = -1;
-				continue;
-			}
-			co.sync();
-			if (co.lane == 0) {
-				FR(fi, 5) = vcnt;
-				FR(fi, 6) = extCnt;
-				FR(fi, 8) = 1;
-				FR(fi, 9) = walkUncov;
-				FR(fi, 1) = 2;
-				FR(fi, 7) = v.noff[tag];
-			}
-			co.sync();
-			state = 2;
-		}
-		// ---- state 2: keep walking (.cpp:618-637) ----
-		{
-			int vcnt = FR(fi, 5);
-			int ei = FR(fi, 7);
-			bool pushed = false;
-			while (ei < v.noff[tag + 1]) {
-				int b = v.nidx[ei++];
-				if ((same_strand(v.rs[tag], strand) && same_strand(v.ls[b], strand)) || v.st[b] == v.en[tag] + 1) {
-					int ns = strand;
-					if (v.st[b] > v.en[tag] + 1) ns = v.rs[tag];
-					co.sync();
-					if (co.lane == 0) {
-						FR(fi, 7) = ei;
-						FR(sp, 0) = 1; FR(sp, 1) = 0; FR(sp, 2) = b; FR(sp, 3) = ns; FR(sp, 4) = owner; FR(sp, 5) = vcnt;
-						FR(sp, 6) = FR(fi, 6);
-					}
-					++sp;
-					co.sync();
-					pushed = true;
-					break;
-				}
-			}
-			if (pushed) continue;
-			--sp;
-			ret = -1;
-		}
-	}
-	co.sync();
-	stRef.nStates = st.nStates;
-	stRef.sumExt = st.sumExt;
-	stRef.sumDrop = st.sumDrop;
-	stRef.sumScan = st.sumScan;
-	stRef.nFrames = st.nFrames;
-	stRef.nRoots = st.nRoots;
-	return ret;
 }
-#undef FR
+
+} // namespace pscdev
+#include "k_dp_walk.cuh"
+namespace pscdev {
+
 
 // copy a memo entry into one of the two "best so far" registers kept in work[] (SetDpContent)
 struct DpBest {
@@ -1044,6 +679,8 @@ PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
 	double *fdbeta = cv.take<double>((size_t)n + 3);
 	int *fdmeta = cv.take<int>((size_t)(n + 3) * 4);
 	uint64_t *fdbits = cv.take<uint64_t>((size_t)(n + 3) * W);
+	uint64_t *fdkey = cv.take<uint64_t>((size_t)(n + 3) * W);
+	uint64_t *pbits = cv.take<uint64_t>((size_t)(n + 4) * W);
 	uint64_t *work = cv.take<uint64_t>((size_t)8 * W);
 	if (cv.off > smBytes) return;
 	d.P = P;
@@ -1052,6 +689,8 @@ PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
 	d.fdbeta = fdbeta;
 	d.fdmeta = fdmeta;
 	d.fdbits = fdbits;
+	d.fdkey = fdkey;
+	d.pbits = pbits;
 	d.work = work;
 }
 
