@@ -786,10 +786,14 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 			supportCnt = co.sum(ls);
 		}
 		co.sync();
-		// phase B, sequential in pair order: accumulate, and redistribute support for pairs that were
-		// already depleted and that this candidate never got a share of (.cpp:1976-2054)
-		if (co.lane == 0) {
+		// phase B, in pair order with all lanes in lockstep: accumulate, and redistribute support for
+		// pairs that were already depleted and that this candidate never got a share of (.cpp:1976-2054).
+		// Pairs are visited sequentially (whether an owner still has abundance depends on the pairs
+		// before); inside one pair the lanes take one row owner each and the fp64 take-out sum is
+		// folded in owner order.
+		{
 			double abm = sc.abund[maxtag];
+			const double tam = sc.tAbund[maxtag];
 			for (int w = 0; w < MW; ++w) {
 				uint64_t word = btm[w];
 				while (word) {
@@ -799,17 +803,23 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 					if (cj >= 0) {
 						abm += cj;
 					} else if (rowm[j] == 0) {
+						// rowm[j] == 0 here, so (csupport[i][j] + rowm[j]) * a / (a + b) - rowm[j] is csupport * a / (a + b).
+						// Only candidates that were picked before can have abundance > 0: walk the (index-sorted)
+						// list of row owners instead of all A candidates.
 						double takeOut = 0, factor = t.pec[j];
-						int listCnt = 0;
-						// only candidates that were picked before can have abundance > 0: walk the (index-sorted)
-						// list of row owners instead of all A candidates
-						for (int pq = 0; pq < poolUsed; ++pq) {
-							int i = sc.picked[pq];
-							if (i == maxtag) continue;
-							if (sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
-								double ci = sc.slot[i] >= 0 ? sc.pool[(long long)sc.slot[i] * M + j] : 0.0;
-								double tmp = (ci + rowm[j]) * sc.tAbund[maxtag] / (sc.tAbund[maxtag] + sc.tAbund[i]) - rowm[j];
-								if (tmp > 0) { sc.list[listCnt++] = i; takeOut += tmp; }
+						for (int p0 = 0; p0 < poolUsed; p0 += co.n) {
+							int pq = p0 + co.lane;
+							double tmp = 0;
+							if (pq < poolUsed) {
+								int i = sc.picked[pq];
+								if (i != maxtag && sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j))
+									tmp = sc.pool[(long long)sc.slot[i] * M + j] * tam / (tam + sc.tAbund[i]);
+							}
+							uint32_t m = co.ballot(tmp > 0);
+							while (m) {
+								int bsrc = ctz32(m);
+								m &= m - 1;
+								takeOut += co.bcast(tmp, bsrc);
 							}
 						}
 						double ratio = 1, takeOutFactor = 0.5;
@@ -820,23 +830,31 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 							if (takeOut > (t.psup[j] * factor) * takeOutFactor)
 								ratio = (t.psup[j] * factor) * takeOutFactor / takeOut;
 						}
-						for (int q = 0; q < listCnt; ++q) {
-							int i = sc.list[q];
-							double *ri = sc.pool + (long long)sc.slot[i] * M; // abund > 0 implies it owns a row
-							double tmp = ((ri[j] + rowm[j]) * sc.tAbund[maxtag] / (sc.tAbund[maxtag] + sc.tAbund[i]) - rowm[j]) * ratio;
-							ri[j] -= tmp;
-							sc.abund[i] -= tmp;
-						}
+						if (takeOut > 0)
+							for (int pq = co.lane; pq < poolUsed; pq += co.n) {
+								int i = sc.picked[pq];
+								if (i != maxtag && sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
+									double *ri = sc.pool + (long long)sc.slot[i] * M;
+									double tmp = ri[j] * tam / (tam + sc.tAbund[i]);
+									if (tmp > 0) {
+										tmp *= ratio;
+										ri[j] -= tmp;
+										sc.abund[i] -= tmp;
+									}
+								}
+							}
 						double tmp = takeOut * ratio;
-						rowm[j] += tmp;
+						if (co.lane == 0) rowm[j] += tmp;
 						abm += tmp;
 					}
 				}
 			}
-			sc.abund[maxtag] = abm;
-			// tc[updateTag].abundance = 0 (.cpp:2063); when it is not one of maxtag's pairs (no pair was
-			// left: update == inf) the reference zeroes pair 0 without touching coverCnt and stops.
-			sc.pairAbund[updateTag] = 0;
+			if (co.lane == 0) {
+				sc.abund[maxtag] = abm;
+				// tc[updateTag].abundance = 0 (.cpp:2063); when it is not one of maxtag's pairs (no pair was
+				// left: update == inf) the reference zeroes pair 0 without touching coverCnt and stops.
+				sc.pairAbund[updateTag] = 0;
+			}
 		}
 		co.sync();
 		deplCnt = *dcount;

@@ -27,6 +27,7 @@ namespace pscdev {
 static inline int popc32(uint32_t x) { return __builtin_popcount(x); }
 static inline int popc64(uint64_t x) { return __builtin_popcountll(x); }
 static inline int ctz64(uint64_t x) { return __builtin_ctzll(x); }
+static inline int ctz32(uint32_t x) { return __builtin_ctz(x); }
 static inline uint64_t brev64(uint64_t x)
 {
 	x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
@@ -38,6 +39,7 @@ static inline uint64_t brev64(uint64_t x)
 PSC_DEV int popc32(uint32_t x) { return __popc(x); }
 PSC_DEV int popc64(uint64_t x) { return __popcll(x); }
 PSC_DEV int ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
+PSC_DEV int ctz32(uint32_t x) { return __ffs((int)x) - 1; }
 PSC_DEV uint64_t brev64(uint64_t x) { return __brevll(x); }
 #endif
 
