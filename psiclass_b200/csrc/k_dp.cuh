@@ -219,6 +219,89 @@ PSC_DEV double dp_scan_cover(const DpState &st, const uint64_t *tb, int tf, int 
 	return cover + cnt;
 }
 
+// ---- components of <= 128 subexons: bit vectors as two registers ----
+// mask of the bits [s, e] of a 128-bit vector (0 <= s, e <= 127; garbage when s > e, callers exclude that)
+PSC_DEV void range2(int s, int e, uint64_t &m0, uint64_t &m1)
+{
+	uint64_t lo0 = s < 64 ? ~(uint64_t)0 << (s & 63) : 0;
+	uint64_t lo1 = s <= 64 ? ~(uint64_t)0 : ~(uint64_t)0 << ((s - 64) & 63);
+	uint64_t hi0 = e >= 63 ? ~(uint64_t)0 : ~(uint64_t)0 >> ((63 - e) & 63);
+	uint64_t hi1 = e < 64 ? 0 : ~(uint64_t)0 >> ((127 - e) & 63);
+	m0 = lo0 & hi0;
+	m1 = lo1 & hi1;
+}
+
+// compat() for W <= 2 without loops or early exits: same decisions, see the case analysis there
+PSC_DEV int compat2(uint64_t ta, uint64_t tb, int tf, int tl, bool tpartial, uint64_t ca, uint64_t cb, int cf, int cl)
+{
+	bool part = cl > tl;
+	int e = part ? tl : cl;
+	uint64_t m0, m1;
+	range2(cf, e, m0, m1);
+	bool tcf = ((cf < 64 ? ta : tb) >> (cf & 63)) & 1;
+	bool tcl = ((cl < 64 ? ta : tb) >> (cl & 63)) & 1;
+	bool ok = cf >= tf && cf <= tl && tcf && (tpartial || (tcl && !part));
+	// a constraint has no bits below its first subexon, so keep(0, e) and keep(cf, e) select the same bits of it
+	uint64_t xa = part ? (ca & m0) : ca, xb = part ? (cb & m1) : cb;
+	ok = ok && (ta & m0) == xa && (tb & m1) == xb;
+	return ok ? (part ? 2 : 1) : 0;
+}
+
+// dp_scan_cover for W <= 2: path bits in registers, two constraints per lane and pass so that their
+// loads and tests overlap; the per-constraint decisions are selects, not branches
+PSC_DEV double dp_scan_cover2(const DpState &st, uint64_t ta, uint64_t tb, int tf, int tl, int tcStart, int bound, double cover,
+                              bool &belowMin, double &beta)
+{
+	int end = dp_tc_end(st, tcStart, bound);
+	if (end <= tcStart) return cover;
+	const DpScratch &d = st.d;
+	const int W = st.W, L = st.co.n;
+	const double minAb = st.minAbundance;
+	bool below = false;
+	int cnt = 0, ccnt = 0;
+	double mn = 1e300, mnAll = 1e300;
+	for (int i0 = tcStart + st.co.lane; i0 < end; i0 += 2 * L) {
+		int i1 = i0 + L;
+		bool v1 = i1 < end;
+		if (!v1) i1 = i0;
+		int f0 = d.tcf[i0], l0 = d.tcl[i0], f1 = d.tcf[i1], l1 = d.tcl[i1];
+		uint64_t a0 = d.tcb[(long long)i0 * W], a1 = d.tcb[(long long)i1 * W];
+		uint64_t b0 = W == 2 ? d.tcb[(long long)i0 * W + 1] : 0, b1 = W == 2 ? d.tcb[(long long)i1 * W + 1] : 0;
+		double n0 = d.tcnorm[i0], n1 = d.tcnorm[i1], x0 = d.tcab[i0], x1 = d.tcab[i1];
+		bool c0 = compat2(ta, tb, tf, tl, false, a0, b0, f0, l0) == 1;
+		bool c1 = v1 && compat2(ta, tb, tf, tl, false, a1, b1, f1, l1) == 1;
+		bool lo0 = n0 <= minAb, lo1 = n1 <= minAb;
+		below = below || (c0 && lo0) || (c1 && lo1);
+		bool in0 = c0 && !lo0, in1 = c1 && !lo1;
+		ccnt += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+		if (in0 && n0 < mnAll) mnAll = n0;
+		if (in1 && n1 < mnAll) mnAll = n1;
+		bool p0 = in0 && x0 > 0, p1 = in1 && x1 > 0;
+		cnt += (p0 ? 1 : 0) + (p1 ? 1 : 0);
+		if (p0 && n0 < mn) mn = n0;
+		if (p1 && n1 < mn) mn = n1;
+	}
+	// the reference breaks at the FIRST compatible constraint with normAbund <= minAbundance, whatever
+	// was counted before, and returns -2: "any" is enough
+	if (st.co.any(below)) {
+		belowMin = true;
+		return -2;
+	}
+	if (!st.forAbundance && st.co.sum(ccnt) > 0) {
+		mnAll = st.co.min_nonneg(mnAll);
+		if (mnAll < beta) beta = mnAll;
+	}
+	cnt = st.co.sum(cnt);
+	if (st.forAbundance) {
+		if (cnt > 0) {
+			mn = st.co.min_nonneg(mn);
+			if (cover == 0 || mn < cover) cover = mn;
+		}
+		return cover;
+	}
+	return cover + cnt;
+}
+
 PSC_DEV void dp_bits_from_path(const DpState &st, uint64_t *dst, const int *p, int cnt, bool clear)
 {
 	// uniform scalar code executed by lane 0 only; callers sync

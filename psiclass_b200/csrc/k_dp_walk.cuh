@@ -4,25 +4,32 @@
 // The reference recurses: SolveSubTranscript(key) tries every successor of the key's last subexon
 // with SearchSubTranscript, which extends the walk subexon by subexon and, wherever no pending
 // constraint reaches further, calls SolveSubTranscript on the walk as a new key.  Here
-//   * an "owner" is one active SolveSubTranscript call (its key lives in the path array P, its
-//     best-so-far path `pdp` in the fd* arrays, one slot per nesting level);
-//   * the walk below an owner is a plain depth-first iteration over path positions: per position
-//     only (strand, successor iterator, #pending extensions, #uncovered edges, path bits) are kept,
-//     and they are written to memory only when the position is descended from or a nested owner is
-//     pushed -- a leaf (memo hit or dead end), which is the common case, costs no frame traffic;
-//   * path bit vectors are built incrementally (parent bits | new subexon) instead of from the path.
+//   * an "owner" is one active SolveSubTranscript call.  The top owner lives in registers (key
+//     range, scan start, extension list, best-so-far path `pdp`); it is written to its slot in the
+//     fd*/OWN arrays only when a nested owner is pushed on top of it;
+//   * the walk below an owner is a plain depth-first iteration over path positions.  The current
+//     position and the child being visited are registers too: (node, strand, successor iterator,
+//     #pending extensions, #uncovered edges, running key hash, path bits).  They go to memory only when
+//     the walk descends or a nested owner is pushed -- a leaf (memo hit or dead end), the common
+//     case, touches no frame memory at all;
+//   * everything a nested key needs is derived incrementally from the walk: its bits are
+//     (child bits & ~owner key bits), its memo hash is the running hash, its count of uncovered
+//     edges a difference of two running counts;
+//   * SMALL (component of <= 128 subexons, W <= 2) keeps all bit vectors in registers and uses the
+//     loop-free compat2 / two-constraints-per-lane scans; wider components go through memory.
 // Depth-first order, strand rules and the strict '>' fold are the reference's, so results are
 // bit-identical (tests/: oracle parity on enumerate + DP sets).
 #pragma once
 
 namespace pscdev {
 
-// per position: 0 strand, 1 successor iterator, 2 extCnt, 3 walkUncov
-#define PPOS(p, k) pp[(p) * 4 + (k)]
-// per owner: 0 vbase 1 vcnt 2 strand 3 tcStart 4 extBase 5 extCnt 6 successor iterator of the key's last node 7 keyUncov
-#define OWN(o, k) of[(o) * 8 + (k)]
+// per walk position: 0 strand, 1 successor iterator, 2 extCnt, 3 walkUncov, 4 running key hash
+#define PPOS(p, k) pp[(p) * 5 + (k)]
+// per owner: 0 vbase 1 vcnt 2 strand 3 tcStart 4 extBase 5 extCnt 6 successor iterator of the key's last node
+//            7 keyUncov 8 memo index 9 strand of the best path
+#define OWN(o, k) of[(o) * 10 + (k)]
 
-PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
+template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int start)
 {
 	// private copy: see the note in dp_pick about escaped addresses
 	DpState st = stRef;
@@ -30,71 +37,117 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 	const CompView v = st.v;
 	const DpScratch d = st.d;
 	const int W = st.W;
+	const uint32_t nn = (uint32_t)v.n;
 	int *const P = d.P;
 	int *const pp = d.fr;
-	int *const of = d.fr + (v.n + 4) * 4;
+	int *const of = d.fr + (v.n + 4) * 5;
 	uint64_t *const pbits = d.pbits; // [(n+4)*W] owner key | walk up to the position
 	uint64_t *const kbits = d.fdkey; // [(n+3)*W] key bits per owner
-	uint64_t subl[2], cbl[2];
-	uint64_t *sub = W <= 2 ? subl : d.work + 2 * W; // scratch path bits (the reference's bufferTxpt)
-	uint64_t *cb = W <= 2 ? cbl : d.work + 4 * W;    // bits of the child position being visited
+	// wide components: scratch path bits (the reference's bufferTxpt) and the bits of the child being visited
+	uint64_t *const sub = d.work + 2 * W;
+	uint64_t *const cb = d.work + 4 * W;
+	const int e0 = v.noff[0];
 	int extTop = 0;
 	int ok = -1; // top of the owner stack
 	long long ret = -1;
 	++st.nRoots;
 
-	// ---- registers describing the current owner and the current position ----
-	int o_vbase = 0, o_vcnt = 0, o_strand = 0, o_tcStart = 0, o_extBase = 0, o_extCnt = 0, o_keyUncov = 0;
+	// ---- the top owner ----
+	int o_vbase = 0, o_vcnt = 0, o_strand = 0, o_tcStart = 0, o_extBase = 0, o_extCnt = 0, o_keyUncov = 0, o_ei = 0;
+	int o_first = 0, o_last = 0;
 	long long o_mi = -1;
-	int cp = 0, c_strand = 0, c_ei = 0, c_ext = 0, c_uncov = 0;
-	// pending child (used across a nested solve)
-	int np = 0, n_strand = 0, n_ext = 0, n_uncov = 0;
+	uint64_t o_ka = 0, o_kb = 0;         // key bits
+	double o_cover = -1, o_beta = 1e300; // pdp
+	uint64_t o_pa = 0, o_pb = 0;
+	int o_plast = 0, o_pstrand = 0;
+	// ---- the current position and the child being visited ----
+	int cp = 0, c_node = 0, c_strand = 0, c_ei = 0, c_ext = 0, c_uncov = 0;
+	uint32_t c_hash = 0;
+	uint64_t c_ba = 0, c_bb = 0;
+	int np = 0, n_node = 0, n_strand = 0, n_ext = 0, n_uncov = 0;
+	uint32_t n_hash = 0;
+	uint64_t n_ba = 0, n_bb = 0;
 	bool keepSearch = false;
+
+	// request: new owner with key P[nvbase .. nvbase+nvcnt)
+	int nvbase = 0, nvcnt = 1, nstrand = 0, ntcStart = 0, nfirst = start, nlast = start, nkeyUncov = 0;
+	uint32_t nhash = 0;
+	uint64_t nka = start < 64 ? (uint64_t)1 << start : 0, nkb = (start >= 64 && start < 128) ? (uint64_t)1 << (start - 64) : 0;
+	int mode = 0; // 0 enter owner, 1 next child of (owner, cp), 2 evaluate child np, 4 owner done
 
 	co.sync();
 	if (co.lane == 0) P[0] = start;
 	co.sync();
-	// request: new owner with key P[nvbase .. nvbase+nvcnt)
-	int nvbase = 0, nvcnt = 1, nstrand = 0, ntcStart = 0;
-	int mode = 0; // 0 enter owner, 1 next child of (owner, cp), 2 evaluate child np
 
+	long long tmark = clock64();
+	int lastMode = 0;
+#define PSC_DP_TICK(m)                                                                                          \
+	{                                                                                                           \
+		long long tn = clock64();                                                                               \
+		if (lastMode == 0) st.sumExt += tn - tmark;                                                             \
+		else if (lastMode == 1) st.sumDrop += tn - tmark;                                                       \
+		else st.sumScan += tn - tmark;                                                                          \
+		tmark = tn;                                                                                             \
+		lastMode = (m);                                                                                         \
+	}
 	for (;;) {
+		PSC_DP_TICK(mode == 0 ? 0 : (mode == 1 ? 1 : 2))
 		if (mode == 0) {
 			// =========== SolveSubTranscript(key) ===========
 			const int *key = P + nvbase;
-			long long mi = dp_memo_index(st, key, nvcnt);
+			long long mi;
+			if (nvcnt == 1) mi = nlast;
+			else if (nvcnt == 2) mi = d.f2Base + (long long)nfirst * v.n + nlast; // seCnt <= 10000 is enforced by the host
+			else mi = d.hashBase + nhash;
 			DpMemo *me = d.ent + mi;
 			uint64_t *mbits = d.ebits + mi * W;
-			// key bits: needed for the hash probe and as the start of every path below this owner
-			dp_build_sub(st, sub, nullptr, key, nvcnt, nullptr, 0);
+			if (!SMALL) dp_build_sub(st, sub, nullptr, key, nvcnt, nullptr, 0);
 			bool hit = false;
 			if (dp_memo_hit(st, me, nstrand)) {
 				if (nvcnt <= 2) hit = true;
-				else if (me->cnt == nvcnt && me->first == key[0]) {
-					bool same = true;
-					int lo = key[0], hi = key[nvcnt - 1];
-					for (int w = lo >> 6; w <= (hi >> 6) && same; ++w)
-						if ((mbits[w] & keep_mask(w, lo, hi)) != sub[w]) same = false;
-					hit = same;
+				else if (me->cnt == nvcnt && me->first == nfirst) {
+					if (SMALL) {
+						uint64_t ra, rb;
+						range2(nfirst, nlast, ra, rb);
+						hit = (mbits[0] & ra) == nka && (W < 2 || (mbits[1] & rb) == nkb);
+					} else {
+						bool same = true;
+						for (int w = nfirst >> 6; w <= (nlast >> 6) && same; ++w)
+							if ((mbits[w] & keep_mask(w, nfirst, nlast)) != sub[w]) same = false;
+						hit = same;
+					}
 				}
 			}
 			if (hit) {
 				ret = mi;
 				if (ok < 0) break; // the root itself was memoised
-				mode = 3;          // return into the owner below
+				mode = 2;          // return into the owner
 				continue;
 			}
 			++st.nStates;
 			// ---- fresh evaluation: this key becomes the new top owner ----
 			if (ok >= 0) {
-				// park the owner below: its position registers go to memory
+				// park the owner below, its current position and the child that became the key's end
+				if (cp == o_vbase + o_vcnt - 1) o_ei = c_ei;
 				co.sync();
 				if (co.lane == 0) {
-					if (cp == o_vbase + o_vcnt - 1) OWN(ok, 6) = c_ei;
-					else PPOS(cp, 1) = c_ei;
+					if (cp != o_vbase + o_vcnt - 1) PPOS(cp, 1) = c_ei;
+					OWN(ok, 6) = o_ei;
+					OWN(ok, 9) = o_pstrand;
+					d.fdcover[ok] = o_cover;
+					d.fdbeta[ok] = o_beta;
+					d.fdmeta[ok * 4 + 1] = o_plast;
+					if (SMALL) {
+						d.fdbits[(long long)ok * W] = o_pa;
+						if (W == 2) d.fdbits[(long long)ok * W + 1] = o_pb;
+						pbits[(long long)np * W] = n_ba;
+						if (W == 2) pbits[(long long)np * W + 1] = n_bb;
+					}
+					P[np] = n_node;
 					PPOS(np, 0) = n_strand;
 					PPOS(np, 2) = n_ext;
 					PPOS(np, 3) = n_uncov;
+					PPOS(np, 4) = (int)n_hash;
 				}
 			}
 			++ok;
@@ -102,33 +155,59 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 			o_vcnt = nvcnt;
 			o_strand = nstrand;
 			o_mi = mi;
-			int last = key[nvcnt - 1];
+			o_first = nfirst;
+			o_last = nlast;
+			o_keyUncov = nkeyUncov;
+			o_ka = nka;
+			o_kb = nkb;
 			{ // first constraint with first >= key[0]
-				int lo = key[0] > 0 ? d.tcEnd[key[0] - 1] : 0;
+				int lo = o_first > 0 ? d.tcEnd[o_first - 1] : 0;
 				o_tcStart = lo > ntcStart ? lo : ntcStart;
 			}
-			o_keyUncov = 0;
-			for (int i = 0; i + 1 < nvcnt; ++i)
-				if (dp_edge_uncovered(st, key[i], key[i + 1])) ++o_keyUncov;
 			double cover = -1, beta0 = 1e300;
-			if (st.ce[last]) {
+			if (st.ce[o_last]) {
 				bool bm = false;
-				cover = dp_scan_cover(st, sub, key[0], last, o_tcStart, last, 0, bm, beta0);
+				if (SMALL) cover = dp_scan_cover2(st, o_ka, o_kb, o_first, o_last, o_tcStart, o_last, 0, bm, beta0);
+				else cover = dp_scan_cover(st, sub, o_first, o_last, o_tcStart, o_last, 0, bm, beta0);
 			}
 			// extensions: constraints whose head matches the tail of the partial path
 			o_extBase = extTop;
 			o_extCnt = 0;
 			{
-				int end = dp_tc_end(st, o_tcStart, last);
-				for (int b0 = o_tcStart; b0 < end; b0 += co.n) {
-					int i = b0 + co.lane;
-					bool is = i < end && compat(sub, key[0], last, true, d.tcb + (long long)i * W, d.tcf[i], d.tcl[i], W) == 2;
-					uint32_t m = co.ballot(is);
-					if (is) {
-						int p = o_extBase + o_extCnt + co.rank_in(m);
-						if (p < d.extCap) d.ext[p] = i;
+				int end = dp_tc_end(st, o_tcStart, o_last);
+				if (SMALL) {
+					for (int b0 = o_tcStart; b0 < end; b0 += 2 * co.n) {
+						int i0 = b0 + co.lane, i1 = i0 + co.n;
+						bool v0 = i0 < end, v1 = i1 < end;
+						int j0 = v0 ? i0 : end - 1, j1 = v1 ? i1 : end - 1;
+						uint64_t a0 = d.tcb[(long long)j0 * W], a1 = d.tcb[(long long)j1 * W];
+						uint64_t b0w = W == 2 ? d.tcb[(long long)j0 * W + 1] : 0, b1w = W == 2 ? d.tcb[(long long)j1 * W + 1] : 0;
+						bool is0 = v0 && compat2(o_ka, o_kb, o_first, o_last, true, a0, b0w, d.tcf[j0], d.tcl[j0]) == 2;
+						bool is1 = v1 && compat2(o_ka, o_kb, o_first, o_last, true, a1, b1w, d.tcf[j1], d.tcl[j1]) == 2;
+						uint32_t m0 = co.ballot(is0);
+						if (is0) {
+							int p = o_extBase + o_extCnt + co.rank_in(m0);
+							if (p < d.extCap) d.ext[p] = i0;
+						}
+						o_extCnt += popc32(m0);
+						uint32_t m1 = co.ballot(is1);
+						if (is1) {
+							int p = o_extBase + o_extCnt + co.rank_in(m1);
+							if (p < d.extCap) d.ext[p] = i1;
+						}
+						o_extCnt += popc32(m1);
 					}
-					o_extCnt += popc32(m);
+				} else {
+					for (int b0 = o_tcStart; b0 < end; b0 += co.n) {
+						int i = b0 + co.lane;
+						bool is = i < end && compat(sub, o_first, o_last, true, d.tcb + (long long)i * W, d.tcf[i], d.tcl[i], W) == 2;
+						uint32_t m = co.ballot(is);
+						if (is) {
+							int p = o_extBase + o_extCnt + co.rank_in(m);
+							if (p < d.extCap) d.ext[p] = i;
+						}
+						o_extCnt += popc32(m);
+					}
 				}
 				if (o_extBase + o_extCnt > d.extCap) {
 					*st.err = 21;
@@ -138,31 +217,35 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 				dp_sort_ext(st, d.ext + o_extBase, o_extCnt, o_extBase + 2 * o_extCnt <= d.extCap);
 			}
 			extTop = o_extBase + o_extCnt;
+			// pdp starts as the key itself
+			o_cover = cover;
+			o_beta = beta0;
+			o_pa = o_ka;
+			o_pb = o_kb;
+			o_plast = o_last;
+			o_pstrand = o_strand;
 			if (co.lane == 0) {
-				uint64_t *vb = d.fdbits + (long long)ok * W, *kb = kbits + (long long)ok * W;
-				for (int w = 0; w < W; ++w) { vb[w] = sub[w]; kb[w] = sub[w]; }
-				d.fdcover[ok] = cover;
-				d.fdbeta[ok] = beta0;
-				d.fdmeta[ok * 4 + 0] = key[0];
-				d.fdmeta[ok * 4 + 1] = last;
-				d.fdmeta[ok * 4 + 2] = o_strand;
+				if (SMALL) {
+					kbits[(long long)ok * W] = o_ka;
+					if (W == 2) kbits[(long long)ok * W + 1] = o_kb;
+				} else {
+					uint64_t *vb = d.fdbits + (long long)ok * W, *kb = kbits + (long long)ok * W;
+					for (int w = 0; w < W; ++w) { vb[w] = sub[w]; kb[w] = sub[w]; }
+				}
 				OWN(ok, 0) = o_vbase; OWN(ok, 1) = o_vcnt; OWN(ok, 2) = o_strand; OWN(ok, 3) = o_tcStart;
-				OWN(ok, 4) = o_extBase; OWN(ok, 5) = o_extCnt; OWN(ok, 7) = o_keyUncov;
+				OWN(ok, 4) = o_extBase; OWN(ok, 5) = o_extCnt; OWN(ok, 7) = o_keyUncov; OWN(ok, 8) = (int)o_mi;
 			}
 			co.sync();
 			cp = o_vbase + o_vcnt - 1;
+			c_node = o_last;
 			c_strand = o_strand;
-			c_ei = v.noff[last];
+			c_ei = v.noff[o_last];
 			c_ext = o_extCnt;
 			c_uncov = o_keyUncov;
+			c_hash = 0;
+			c_ba = o_ka;
+			c_bb = o_kb;
 			mode = 1;
-			continue;
-		}
-		if (mode == 3) {
-			// =========== a nested SolveSubTranscript returned `ret`: resume the owner below ===========
-			// (ok is the owner that issued the request; its registers may be stale only if a fresh
-			// evaluation happened in between, in which case they were parked above)
-			mode = 2;
 			continue;
 		}
 		if (mode == 4) {
@@ -171,13 +254,18 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 			uint64_t *mbits = d.ebits + o_mi * W;
 			co.sync();
 			if (co.lane == 0) {
-				const uint64_t *vb = d.fdbits + (long long)ok * W;
-				for (int w = 0; w < W; ++w) mbits[w] = vb[w];
-				me->first = d.fdmeta[ok * 4 + 0];
-				me->last = d.fdmeta[ok * 4 + 1];
-				me->strand = d.fdmeta[ok * 4 + 2];
-				me->cover = d.fdcover[ok];
-				me->beta = d.fdbeta[ok];
+				if (SMALL) {
+					mbits[0] = o_pa;
+					if (W == 2) mbits[1] = o_pb;
+				} else {
+					const uint64_t *vb = d.fdbits + (long long)ok * W;
+					for (int w = 0; w < W; ++w) mbits[w] = vb[w];
+				}
+				me->first = o_first;
+				me->last = o_plast;
+				me->strand = o_pstrand;
+				me->cover = o_cover;
+				me->beta = o_beta;
 				me->iter = st.iter;
 				me->mode = st.forAbundance ? 1 : 0;
 				me->cnt = o_vcnt;
@@ -191,23 +279,40 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 			int keyEnd = o_vbase + o_vcnt - 1; // == the child position np of the owner below
 			--ok;
 			if (ok < 0) break;
-			// reload the owner below and the position it was working at
+			// reload the owner below, the position it was working at and the child that was the key's end
 			o_vbase = OWN(ok, 0); o_vcnt = OWN(ok, 1); o_strand = OWN(ok, 2); o_tcStart = OWN(ok, 3);
-			o_extBase = OWN(ok, 4); o_extCnt = OWN(ok, 5); o_keyUncov = OWN(ok, 7);
-			o_mi = dp_memo_index(st, P + o_vbase, o_vcnt);
+			o_extBase = OWN(ok, 4); o_extCnt = OWN(ok, 5); o_ei = OWN(ok, 6); o_keyUncov = OWN(ok, 7);
+			o_mi = OWN(ok, 8); o_pstrand = OWN(ok, 9);
+			o_first = P[o_vbase];
+			o_last = P[o_vbase + o_vcnt - 1];
+			o_cover = d.fdcover[ok];
+			o_beta = d.fdbeta[ok];
+			o_plast = d.fdmeta[ok * 4 + 1];
+			if (SMALL) {
+				o_ka = kbits[(long long)ok * W];
+				o_kb = W == 2 ? kbits[(long long)ok * W + 1] : 0;
+				o_pa = d.fdbits[(long long)ok * W];
+				o_pb = W == 2 ? d.fdbits[(long long)ok * W + 1] : 0;
+			}
 			np = keyEnd;
+			n_node = P[np];
+			n_strand = PPOS(np, 0); n_ext = PPOS(np, 2); n_uncov = PPOS(np, 3); n_hash = (uint32_t)PPOS(np, 4);
 			cp = np - 1;
 			if (cp == o_vbase + o_vcnt - 1) {
-				c_strand = o_strand; c_ei = OWN(ok, 6); c_ext = o_extCnt; c_uncov = o_keyUncov;
+				c_node = o_last; c_strand = o_strand; c_ei = o_ei; c_ext = o_extCnt; c_uncov = o_keyUncov; c_hash = 0;
+				c_ba = o_ka; c_bb = o_kb;
 			} else {
-				c_strand = PPOS(cp, 0); c_ei = PPOS(cp, 1); c_ext = PPOS(cp, 2); c_uncov = PPOS(cp, 3);
+				c_node = P[cp];
+				c_strand = PPOS(cp, 0); c_ei = PPOS(cp, 1); c_ext = PPOS(cp, 2); c_uncov = PPOS(cp, 3); c_hash = (uint32_t)PPOS(cp, 4);
+				if (SMALL) {
+					c_ba = pbits[(long long)cp * W];
+					c_bb = W == 2 ? pbits[(long long)cp * W + 1] : 0;
+				}
 			}
-			n_strand = PPOS(np, 0); n_ext = PPOS(np, 2); n_uncov = PPOS(np, 3);
 			keepSearch = false;
-			// child bits were parked in pbits[np]
-			if (W <= 2) {
-				cb[0] = pbits[(long long)np * W];
-				if (W == 2) cb[1] = pbits[(long long)np * W + 1];
+			if (SMALL) {
+				n_ba = pbits[(long long)np * W];
+				n_bb = W == 2 ? pbits[(long long)np * W + 1] : 0;
 			} else {
 				co.sync();
 				if (co.lane == 0)
@@ -219,14 +324,19 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 		}
 		if (mode == 1) {
 			// =========== next successor of position cp (SearchSubTranscript's loops, .cpp:618-637, 798-819) ===========
-			int a = P[cp];
+			const int a = c_node;
 			int b = -1, ns = c_strand;
-			while (c_ei < v.noff[a + 1]) {
-				int x = v.nidx[c_ei++];
-				if ((same_strand(v.rs[a], c_strand) && same_strand(v.ls[x], c_strand)) || v.st[x] == v.en[a] + 1) {
-					b = x;
-					if (v.st[x] > v.en[a] + 1) ns = v.rs[a];
-					break;
+			{
+				const int eEnd = v.noff[a + 1], rsa = v.rs[a], ena = v.en[a];
+				const bool aOk = same_strand(rsa, c_strand);
+				while (c_ei < eEnd) {
+					int x = v.nidx[c_ei++];
+					int stx = v.st[x];
+					if ((aOk && same_strand(v.ls[x], c_strand)) || stx == ena + 1) {
+						b = x;
+						if (stx > ena + 1) ns = rsa;
+						break;
+					}
 				}
 			}
 			if (b < 0) {
@@ -237,63 +347,75 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 				}
 				--cp;
 				if (cp == o_vbase + o_vcnt - 1) {
-					c_strand = o_strand; c_ei = OWN(ok, 6); c_ext = o_extCnt; c_uncov = o_keyUncov;
+					c_node = o_last; c_strand = o_strand; c_ei = o_ei; c_ext = o_extCnt; c_uncov = o_keyUncov; c_hash = 0;
+					c_ba = o_ka; c_bb = o_kb;
 				} else {
-					c_strand = PPOS(cp, 0); c_ei = PPOS(cp, 1); c_ext = PPOS(cp, 2); c_uncov = PPOS(cp, 3);
+					c_node = P[cp];
+					c_strand = PPOS(cp, 0); c_ei = PPOS(cp, 1); c_ext = PPOS(cp, 2); c_uncov = PPOS(cp, 3); c_hash = (uint32_t)PPOS(cp, 4);
+					if (SMALL) {
+						c_ba = pbits[(long long)cp * W];
+						c_bb = W == 2 ? pbits[(long long)cp * W + 1] : 0;
+					}
 				}
 				continue;
 			}
 			// ---- visit child b at position np = cp + 1 (SearchSubTranscript entry, .cpp:385-422) ----
 			++st.nFrames;
 			np = cp + 1;
+			n_node = b;
 			n_strand = ns;
-			n_uncov = c_uncov + (dp_edge_uncovered(st, a, b) ? 1 : 0);
+			n_uncov = c_uncov + (d.uncov[c_ei - 1 - e0] ? 1 : 0); // the edge (a, b) is the one the iterator just passed
+			n_hash = (c_hash * nn + (uint32_t)b) % PSC_DP_HASH;
 			// path bits: (key | walk up to cp) | b
-			{
+			if (SMALL) {
+				n_ba = c_ba | (b < 64 ? (uint64_t)1 << b : 0);
+				n_bb = c_bb | (b >= 64 ? (uint64_t)1 << (b - 64) : 0);
+			} else {
 				const uint64_t *src = cp == o_vbase + o_vcnt - 1 ? kbits + (long long)ok * W : pbits + (long long)cp * W;
-				if (W <= 2) {
-					cb[0] = src[0];
-					if (W == 2) cb[1] = src[1];
-					cb[b >> 6] |= (uint64_t)1 << (b & 63);
-				} else {
-					co.sync();
-					if (co.lane == 0) {
-						for (int w = 0; w < W; ++w) cb[w] = src[w];
-						bt_set(cb, b);
-					}
-					co.sync();
+				co.sync();
+				if (co.lane == 0) {
+					for (int w = 0; w < W; ++w) cb[w] = src[w];
+					bt_set(cb, b);
+					// the path array and the parked bits must be in place before anything deeper reads them
+					P[np] = b;
+					for (int w = 0; w < W; ++w) pbits[(long long)np * W + w] = cb[w];
 				}
+				co.sync();
 			}
-			const int *parents = P + o_vbase;
 			// drop the pending extensions that no longer fit (.cpp:407-412)
 			{
 				const int *ext = d.ext + o_extBase;
 				int i;
 				for (i = c_ext - 1; i >= 0; --i) {
 					int x = ext[i];
-					if (d.tcl[x] <= b ||
-					    (bt_test(d.tcb + (long long)x * W, b) &&
-					     compat(cb, parents[0], b, true, d.tcb + (long long)x * W, d.tcf[x], d.tcl[x], W) != 0))
-						break;
+					int xl = d.tcl[x];
+					if (xl <= b) break;
+					if (SMALL) {
+						uint64_t xa = d.tcb[(long long)x * W], xb = W == 2 ? d.tcb[(long long)x * W + 1] : 0;
+						if ((((b < 64 ? xa : xb) >> (b & 63)) & 1) && compat2(n_ba, n_bb, o_first, b, true, xa, xb, d.tcf[x], xl) != 0) break;
+					} else {
+						if (bt_test(d.tcb + (long long)x * W, b) &&
+						    compat(cb, o_first, b, true, d.tcb + (long long)x * W, d.tcf[x], xl, W) != 0)
+							break;
+					}
 				}
 				n_ext = i + 1;
 			}
 			bool solveHere = v.noff[b + 1] > v.noff[b] && (n_ext == 0 || b >= d.tcl[d.ext[o_extBase + n_ext - 1]]);
 			keepSearch = !solveHere;
 			ret = -1;
-			// the path array and the parked bits must be in place before anything deeper reads them
-			co.sync();
-			if (co.lane == 0) {
-				P[np] = b;
-				for (int w = 0; w < W; ++w) pbits[(long long)np * W + w] = cb[w];
-			}
-			co.sync();
 			if (solveHere) {
 				nvbase = o_vbase + o_vcnt;
 				nvcnt = np - nvbase + 1;
 				nstrand = ns;
 				ntcStart = o_tcStart;
-				mode = 0; // answered by the memo (-> mode 3 -> 2) or evaluated as a new owner (-> mode 4 -> 2)
+				nlast = b;
+				nfirst = nvcnt == 1 ? b : P[nvbase];
+				nhash = n_hash;
+				nkeyUncov = nvcnt == 1 ? 0 : n_uncov - PPOS(nvbase, 3);
+				nka = n_ba & ~o_ka;
+				nkb = n_bb & ~o_kb;
+				mode = 0; // answered by the memo (-> mode 2) or evaluated as a new owner (-> mode 4 -> 2)
 				continue;
 			}
 			mode = 2;
@@ -301,10 +423,8 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 		}
 		// =========== mode 2: evaluate child np given the sub-solution `ret` (.cpp:425-614) ===========
 		{
-			const int *parents = P + o_vbase;
-			int pcnt = o_vcnt;
-			int tag = P[np];
-			uint64_t *pb = d.fdbits + (long long)ok * W; // pdp.seVector
+			const int tag = n_node;
+			uint64_t *pb = d.fdbits + (long long)ok * W; // pdp.seVector of wide components
 			double vcover = -1, vbeta = 1e300;
 			const uint64_t *vbits = nullptr;
 			int vlast = -1;
@@ -314,56 +434,60 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 				vbits = d.ebits + ret * W;
 				vlast = d.ent[ret].last;
 			}
-			double pcover = d.fdcover[ok];
 			bool belowMin = false;
 			if (vcover >= 0) {
 				double cover = vcover;
 				// parents | sub-solution
-				{
+				uint64_t sa = 0, sb = 0;
+				if (SMALL) {
+					sa = o_ka | vbits[0];
+					sb = W == 2 ? (o_kb | vbits[1]) : 0;
+				} else {
 					const uint64_t *kb = kbits + (long long)ok * W;
-					if (W <= 2) {
-						sub[0] = kb[0] | vbits[0];
-						if (W == 2) sub[1] = kb[1] | vbits[1];
-					} else {
-						co.sync();
-						if (co.lane == 0)
-							for (int w = 0; w < W; ++w) sub[w] = kb[w] | vbits[w];
-						co.sync();
-					}
+					co.sync();
+					if (co.lane == 0)
+						for (int w = 0; w < W; ++w) sub[w] = kb[w] | vbits[w];
+					co.sync();
 				}
 				if (!st.forAbundance && st.minAbundance > 0 && n_uncov > 0) belowMin = true;
 				bool bm2 = false;
 				double cbeta = vbeta;
-				cover = dp_scan_cover(st, sub, parents[0], vlast, o_tcStart, parents[pcnt - 1], cover, bm2, cbeta);
+				if (SMALL) cover = dp_scan_cover2(st, sa, sb, o_first, vlast, o_tcStart, o_last, cover, bm2, cbeta);
+				else cover = dp_scan_cover(st, sub, o_first, vlast, o_tcStart, o_last, cover, bm2, cbeta);
 				if (bm2) belowMin = true;
-				bool takeBelow = belowMin && pcover == -1;
-				if (takeBelow || (!(belowMin && pcover == -1) && cover > pcover)) {
+				bool takeBelow = belowMin && o_cover == -1;
+				if (takeBelow || (!(belowMin && o_cover == -1) && cover > o_cover)) {
+					o_cover = takeBelow ? -2 : cover;
+					o_beta = cbeta;
+					o_plast = vlast;
+					o_pstrand = n_strand;
+					if (SMALL) {
+						o_pa = sa;
+						o_pb = sb;
+					} else {
+						co.sync();
+						if (co.lane == 0)
+							for (int w = 0; w < W; ++w) pb[w] = sub[w];
+						co.sync();
+					}
+				}
+			} else if (vcover == -2 && o_cover == -1) {
+				o_cover = -2;
+				o_plast = vlast;
+				o_pstrand = n_strand;
+				if (SMALL) {
+					o_pa = vbits[0] | o_ka;
+					o_pb = W == 2 ? (vbits[1] | o_kb) : 0;
+				} else {
 					co.sync();
 					if (co.lane == 0) {
-						d.fdcover[ok] = takeBelow ? -2 : cover;
-						d.fdbeta[ok] = cbeta;
-						for (int w = 0; w < W; ++w) pb[w] = sub[w];
-						d.fdmeta[ok * 4 + 0] = parents[0];
-						d.fdmeta[ok * 4 + 1] = vlast;
-						d.fdmeta[ok * 4 + 2] = n_strand;
+						const uint64_t *kb = kbits + (long long)ok * W;
+						for (int w = 0; w < W; ++w) pb[w] = vbits[w] | kb[w];
 					}
 					co.sync();
-					pcover = takeBelow ? -2 : cover;
 				}
-			} else if (vcover == -2 && pcover == -1) {
-				co.sync();
-				if (co.lane == 0) {
-					const uint64_t *kb = kbits + (long long)ok * W;
-					for (int w = 0; w < W; ++w) pb[w] = vbits[w] | kb[w];
-					d.fdcover[ok] = -2;
-					d.fdmeta[ok * 4 + 0] = parents[0];
-					d.fdmeta[ok * 4 + 1] = vlast;
-					d.fdmeta[ok * 4 + 2] = n_strand;
-				}
-				co.sync();
-				pcover = -2;
 			}
-			// the path may also stop at this subexon (.cpp:524-614): path bits == cb
+			// the path may also stop at this subexon (.cpp:524-614): path bits == the child's bits
 			if (st.ce[tag] && (vcover < 0 || st.forAbundance)) {
 				bool below = false;
 				double cover = 0;
@@ -373,50 +497,75 @@ PSC_DEVN long long dp_solve_root(DpState &stRef, int start)
 				}
 				bool bm2 = false;
 				double cbeta = 1e300;
-				cover = dp_scan_cover(st, cb, parents[0], tag, o_tcStart, tag, cover, bm2, cbeta);
+				if (SMALL) cover = dp_scan_cover2(st, n_ba, n_bb, o_first, tag, o_tcStart, tag, cover, bm2, cbeta);
+				else cover = dp_scan_cover(st, cb, o_first, tag, o_tcStart, tag, cover, bm2, cbeta);
 				if (bm2) below = true;
-				bool takeBelow = below && pcover == -1;
-				if (takeBelow || (!(below && pcover == -1) && cover > pcover)) {
-					co.sync();
-					if (co.lane == 0) {
-						d.fdcover[ok] = takeBelow ? -2 : cover;
-						d.fdbeta[ok] = cbeta;
-						for (int w = 0; w < W; ++w) pb[w] = cb[w];
-						d.fdmeta[ok * 4 + 0] = parents[0];
-						d.fdmeta[ok * 4 + 1] = tag;
-						d.fdmeta[ok * 4 + 2] = n_strand;
+				bool takeBelow = below && o_cover == -1;
+				if (takeBelow || (!(below && o_cover == -1) && cover > o_cover)) {
+					o_cover = takeBelow ? -2 : cover;
+					o_beta = cbeta;
+					o_plast = tag;
+					o_pstrand = n_strand;
+					if (SMALL) {
+						o_pa = n_ba;
+						o_pb = n_bb;
+					} else {
+						co.sync();
+						if (co.lane == 0)
+							for (int w = 0; w < W; ++w) pb[w] = cb[w];
+						co.sync();
 					}
-					co.sync();
 				}
 			}
 			if (keepSearch) {
 				// descend: park cp's iterator, make np the current position
+				if (cp == o_vbase + o_vcnt - 1) o_ei = c_ei;
 				co.sync();
 				if (co.lane == 0) {
-					if (cp == o_vbase + o_vcnt - 1) OWN(ok, 6) = c_ei;
-					else PPOS(cp, 1) = c_ei;
+					if (cp != o_vbase + o_vcnt - 1) PPOS(cp, 1) = c_ei;
+					P[np] = n_node;
 					PPOS(np, 0) = n_strand;
 					PPOS(np, 2) = n_ext;
 					PPOS(np, 3) = n_uncov;
+					PPOS(np, 4) = (int)n_hash;
+					if (SMALL) {
+						pbits[(long long)np * W] = n_ba;
+						if (W == 2) pbits[(long long)np * W + 1] = n_bb;
+					}
 				}
 				co.sync();
 				cp = np;
+				c_node = n_node;
 				c_strand = n_strand;
 				c_ei = v.noff[tag];
 				c_ext = n_ext;
 				c_uncov = n_uncov;
+				c_hash = n_hash;
+				c_ba = n_ba;
+				c_bb = n_bb;
 			}
 			ret = -1;
 			mode = 1;
 		}
 	}
 	co.sync();
+	PSC_DP_TICK(0)
+	stRef.sumExt = st.sumExt;
+	stRef.sumDrop = st.sumDrop;
+	stRef.sumScan = st.sumScan;
 	stRef.nStates = st.nStates;
 	stRef.nFrames = st.nFrames;
 	stRef.nRoots = st.nRoots;
 	return ret;
 }
+#undef PSC_DP_TICK
 #undef PPOS
 #undef OWN
+
+PSC_DEVN long long dp_solve_root(DpState &st, int start)
+{
+	if (st.W <= 2) return dp_solve_root_t<true>(st, start);
+	return dp_solve_root_t<false>(st, start);
+}
 
 } // namespace pscdev

@@ -369,7 +369,7 @@ int psc_solve(psc_ctx *ctx)
 				for (int k = 0; k < 12 && k < nUnits; ++k) {
 					int u = ix[(size_t)k];
 					int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
-					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld | Mcyc solve-entry %lld search %lld other %lld\n", u, c, s,
+					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld | Mcyc owner-entry %lld next-child %lld evaluate %lld\n", u, c, s,
 					        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
 					        h[(size_t)u * 8] / 1e6, h[(size_t)u * 8 + 1] & 0xffffffff, h[(size_t)u * 8 + 2] & 0xffffffff, h[(size_t)u * 8 + 3] & 0xfff, (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff, h[(size_t)u * 8 + 3] >> 40,
 					        h[(size_t)u * 8 + 1] >> 32, h[(size_t)u * 8 + 2] >> 32, h[(size_t)u * 8 + 4] >> 20, h[(size_t)u * 8 + 5] >> 20, h[(size_t)u * 8 + 6] >> 20);
