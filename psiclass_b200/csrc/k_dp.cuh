@@ -16,13 +16,15 @@ struct DpMemo {
 	// smallest normAbund among the constraints compatible with the stored path (those the recursion
 	// examined): the entry stays exact for every higher threshold below it, see dp_memo_hit
 	double beta;
-	int first, last, cnt, timeStamp, strand, epoch;
+	int first, last, cnt, timeStamp, strand;
 	int iter, mode; // outer iteration / forAbundance flag the entry was computed under
 };
 
 struct DpScratch {
-	// memo: f1 [n], f2 [n*n], hash [hashMax]; an entry is valid only when epoch matches
+	// memo: f1 [n], f2 [n*n], hash [hashMax]; an entry is valid only when its epoch (kept in an array of
+	// its own, zeroed by the unit before use) matches
 	DpMemo *ent;
+	int *eepoch;
 	uint64_t *ebits;
 	long long f2Base, hashBase;
 	int hashMax;
@@ -71,6 +73,7 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 	long long nEnt = (long long)n + (long long)n * n + s.hashMax;
 	s.f2Base = n;
 	s.hashBase = (long long)n + (long long)n * n;
+	s.eepoch = cv.take<int>((size_t)nEnt);
 	s.ent = cv.take<DpMemo>((size_t)nEnt);
 	s.ebits = cv.take<uint64_t>((size_t)nEnt * W);
 	s.tcb = cv.take<uint64_t>((size_t)Cmax * W + 1);
@@ -114,13 +117,8 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 	if (o) *o = s;
 	return (cv.off + 15) & ~(size_t)15;
 }
-// bytes at the start of the scratch that must be zero before the first use (memo epochs)
-__host__ __device__ inline size_t dp_scratch_zero_bytes(int n)
-{
-	int hashMax = 8191;
-	long long nEnt = (long long)n + (long long)n * n + hashMax;
-	return (size_t)nEnt * sizeof(DpMemo);
-}
+// number of memo entries (the unit zeroes their epochs before the first use)
+__host__ __device__ inline long long dp_memo_entries(int n) { return (long long)n + (long long)n * n + 8191; }
 
 struct DpState {
 	Coop co;
@@ -132,7 +130,8 @@ struct DpState {
 	double minAbundance;
 	int timeStamp, epoch, iter;
 	int *err;
-	mutable long long nStates, nLevels, nIters, nFrames, nRoots, cycRoot, cycAssign, sumExt, sumDrop, sumScan; // instrumentation (PSC_DEBUG_DP)
+	bool prof; // PSC_DEBUG_DP: per-mode cycle counters
+	mutable long long nStates, nLevels, nIters, nFrames, nRoots, cycRoot, cycAssign; // instrumentation (PSC_DEBUG_DP)
 };
 
 PSC_DEV bool dp_edge_uncovered(const DpState &st, int a, int b)
@@ -219,67 +218,150 @@ PSC_DEV double dp_scan_cover(const DpState &st, const uint64_t *tb, int tf, int 
 	return cover + cnt;
 }
 
-// ---- components of <= 128 subexons: bit vectors as two registers ----
-// mask of the bits [s, e] of a 128-bit vector (0 <= s, e <= 127; garbage when s > e, callers exclude that)
-PSC_DEV void range2(int s, int e, uint64_t &m0, uint64_t &m1)
-{
-	uint64_t lo0 = s < 64 ? ~(uint64_t)0 << (s & 63) : 0;
-	uint64_t lo1 = s <= 64 ? ~(uint64_t)0 : ~(uint64_t)0 << ((s - 64) & 63);
-	uint64_t hi0 = e >= 63 ? ~(uint64_t)0 : ~(uint64_t)0 >> ((63 - e) & 63);
-	uint64_t hi1 = e < 64 ? 0 : ~(uint64_t)0 >> ((127 - e) & 63);
-	m0 = lo0 & hi0;
-	m1 = lo1 & hi1;
-}
+// ---- components of <= 256 subexons: bit vectors of W <= NW words held in registers (NW = 2 or 4: few
+// instantiations, because warps of one SM running different copies of the walk thrash the instruction cache) ----
+// (every loop below has a compile-time trip count and is unrolled, so w[] never becomes an array in memory)
+template <int NW> struct BitsR {
+	uint64_t w[NW > 0 ? NW : 1];
+	PSC_DEV void clear()
+	{
+#pragma unroll
+		for (int i = 0; i < NW; ++i) w[i] = 0;
+	}
+	// W <= NW words in memory; the words above W stay zero
+	PSC_DEV void load(const uint64_t *p, int W)
+	{
+#pragma unroll
+		for (int i = 0; i < NW; ++i) w[i] = (i == 0 || i < W) ? p[i < W ? i : 0] : 0;
+	}
+	PSC_DEV void store(uint64_t *p, int W) const
+	{
+#pragma unroll
+		for (int i = 0; i < NW; ++i)
+			if (i == 0 || i < W) p[i] = w[i];
+	}
+	PSC_DEV void set(int q)
+	{
+#pragma unroll
+		for (int i = 0; i < NW; ++i) w[i] |= (q >> 6) == i ? (uint64_t)1 << (q & 63) : 0;
+	}
+	PSC_DEV bool test(int q) const
+	{
+		uint64_t x = w[NW > 0 ? NW - 1 : 0];
+#pragma unroll
+		for (int i = 0; i + 1 < NW; ++i)
+			if ((q >> 6) == i) x = w[i];
+		return (x >> (q & 63)) & 1;
+	}
+	PSC_DEV void or_with(const BitsR &o)
+	{
+#pragma unroll
+		for (int i = 0; i < NW; ++i) w[i] |= o.w[i];
+	}
+	PSC_DEV void and_not(const BitsR &a, const BitsR &b)
+	{
+#pragma unroll
+		for (int i = 0; i < NW; ++i) w[i] = a.w[i] & ~b.w[i];
+	}
+	// mask of the bits [s, e], 0 <= s, e < 64 * NW (empty when s > e)
+	PSC_DEV void range(int s, int e)
+	{
+#pragma unroll
+		for (int i = 0; i < NW; ++i) {
+			const int lo = 64 * i, hi = lo + 63;
+			// bits >= s: all of the word when s <= lo (the shift does that by itself in word 0), none when s > hi
+			uint64_t a = ~(uint64_t)0 << ((s - lo) & 63);
+			if (i > 0 && s <= lo) a = ~(uint64_t)0;
+			if (i + 1 < NW && s > hi) a = 0;
+			// bits <= e: all of the word when e >= hi (the shift does that in the last word), none when e < lo
+			uint64_t b = ~(uint64_t)0 >> ((hi - e) & 63);
+			if (i + 1 < NW && e >= hi) b = ~(uint64_t)0;
+			if (i > 0 && e < lo) b = 0;
+			w[i] = a & b;
+		}
+	}
+	// (*this & m) == x
+	PSC_DEV bool masked_equals(const BitsR &m, const BitsR &x) const
+	{
+		bool eq = true;
+#pragma unroll
+		for (int i = 0; i < NW; ++i) eq = eq && (w[i] & m.w[i]) == x.w[i];
+		return eq;
+	}
+};
 
-// compat() for W <= 2 without loops or early exits: same decisions, see the case analysis there
-PSC_DEV int compat2(uint64_t ta, uint64_t tb, int tf, int tl, bool tpartial, uint64_t ca, uint64_t cb, int cf, int cl)
+// compat() without loops or early exits: same decisions, see the case analysis there
+template <int NW> PSC_DEV int compat_r(const BitsR<NW> &t, int tf, int tl, bool tpartial, const BitsR<NW> &c, int cf, int cl)
 {
 	bool part = cl > tl;
 	int e = part ? tl : cl;
-	uint64_t m0, m1;
-	range2(cf, e, m0, m1);
-	bool tcf = ((cf < 64 ? ta : tb) >> (cf & 63)) & 1;
-	bool tcl = ((cl < 64 ? ta : tb) >> (cl & 63)) & 1;
-	bool ok = cf >= tf && cf <= tl && tcf && (tpartial || (tcl && !part));
+	BitsR<NW> m;
+	m.range(cf, e);
+	bool ok = cf >= tf && cf <= tl && t.test(cf) && (tpartial || (!part && t.test(cl)));
 	// a constraint has no bits below its first subexon, so keep(0, e) and keep(cf, e) select the same bits of it
-	uint64_t xa = part ? (ca & m0) : ca, xb = part ? (cb & m1) : cb;
-	ok = ok && (ta & m0) == xa && (tb & m1) == xb;
-	return ok ? (part ? 2 : 1) : 0;
+	bool eq = true;
+#pragma unroll
+	for (int i = 0; i < NW; ++i) {
+		uint64_t x = part ? (c.w[i] & m.w[i]) : c.w[i];
+		eq = eq && (t.w[i] & m.w[i]) == x;
+	}
+	return ok && eq ? (part ? 2 : 1) : 0;
 }
 
-// dp_scan_cover for W <= 2: path bits in registers, two constraints per lane and pass so that their
-// loads and tests overlap; the per-constraint decisions are selects, not branches
-PSC_DEV double dp_scan_cover2(const DpState &st, uint64_t ta, uint64_t tb, int tf, int tl, int tcStart, int bound, double cover,
-                              bool &belowMin, double &beta)
+// dp_scan_cover with the path bits in registers; the per-constraint decisions are selects, not
+// branches.  Ranges of more than one constraint per lane take two per lane and pass so that their loads
+// and tests overlap.  The warp reductions are kept to one vote, one packed add and -- only when some
+// lane can lower the running minimum -- one minimum.
+template <int NW>
+PSC_DEV double dp_scan_cover_r(const DpState &st, const BitsR<NW> &t, int tf, int tl, int tcStart, int bound, double cover,
+                               bool &belowMin, double &beta)
 {
 	int end = dp_tc_end(st, tcStart, bound);
 	if (end <= tcStart) return cover;
 	const DpScratch &d = st.d;
-	const int W = st.W, L = st.co.n;
+	const int L = st.co.n, W = st.W;
 	const double minAb = st.minAbundance;
 	bool below = false;
 	int cnt = 0, ccnt = 0;
 	double mn = 1e300, mnAll = 1e300;
-	for (int i0 = tcStart + st.co.lane; i0 < end; i0 += 2 * L) {
-		int i1 = i0 + L;
-		bool v1 = i1 < end;
-		if (!v1) i1 = i0;
-		int f0 = d.tcf[i0], l0 = d.tcl[i0], f1 = d.tcf[i1], l1 = d.tcl[i1];
-		uint64_t a0 = d.tcb[(long long)i0 * W], a1 = d.tcb[(long long)i1 * W];
-		uint64_t b0 = W == 2 ? d.tcb[(long long)i0 * W + 1] : 0, b1 = W == 2 ? d.tcb[(long long)i1 * W + 1] : 0;
-		double n0 = d.tcnorm[i0], n1 = d.tcnorm[i1], x0 = d.tcab[i0], x1 = d.tcab[i1];
-		bool c0 = compat2(ta, tb, tf, tl, false, a0, b0, f0, l0) == 1;
-		bool c1 = v1 && compat2(ta, tb, tf, tl, false, a1, b1, f1, l1) == 1;
-		bool lo0 = n0 <= minAb, lo1 = n1 <= minAb;
-		below = below || (c0 && lo0) || (c1 && lo1);
-		bool in0 = c0 && !lo0, in1 = c1 && !lo1;
-		ccnt += (in0 ? 1 : 0) + (in1 ? 1 : 0);
-		if (in0 && n0 < mnAll) mnAll = n0;
-		if (in1 && n1 < mnAll) mnAll = n1;
-		bool p0 = in0 && x0 > 0, p1 = in1 && x1 > 0;
-		cnt += (p0 ? 1 : 0) + (p1 ? 1 : 0);
-		if (p0 && n0 < mn) mn = n0;
-		if (p1 && n1 < mn) mn = n1;
+	if (end - tcStart <= L) {
+		int i0 = tcStart + st.co.lane;
+		if (i0 < end) {
+			BitsR<NW> x;
+			x.load(d.tcb + (long long)i0 * W, W);
+			double n0 = d.tcnorm[i0], x0 = d.tcab[i0];
+			bool c0 = compat_r<NW>(t, tf, tl, false, x, d.tcf[i0], d.tcl[i0]) == 1;
+			bool lo0 = n0 <= minAb;
+			below = c0 && lo0;
+			bool in0 = c0 && !lo0, p0 = in0 && x0 > 0;
+			ccnt = in0 ? 1 : 0;
+			cnt = p0 ? 1 : 0;
+			if (in0) mnAll = n0;
+			if (p0) mn = n0;
+		}
+	} else {
+		for (int i0 = tcStart + st.co.lane; i0 < end; i0 += 2 * L) {
+			int i1 = i0 + L;
+			bool v1 = i1 < end;
+			if (!v1) i1 = i0;
+			int f0 = d.tcf[i0], l0 = d.tcl[i0], f1 = d.tcf[i1], l1 = d.tcl[i1];
+			BitsR<NW> y0, y1;
+			y0.load(d.tcb + (long long)i0 * W, W);
+			y1.load(d.tcb + (long long)i1 * W, W);
+			double n0 = d.tcnorm[i0], n1 = d.tcnorm[i1], x0 = d.tcab[i0], x1 = d.tcab[i1];
+			bool c0 = compat_r<NW>(t, tf, tl, false, y0, f0, l0) == 1;
+			bool c1 = v1 && compat_r<NW>(t, tf, tl, false, y1, f1, l1) == 1;
+			bool lo0 = n0 <= minAb, lo1 = n1 <= minAb;
+			below = below || (c0 && lo0) || (c1 && lo1);
+			bool in0 = c0 && !lo0, in1 = c1 && !lo1;
+			ccnt += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+			if (in0 && n0 < mnAll) mnAll = n0;
+			if (in1 && n1 < mnAll) mnAll = n1;
+			bool p0 = in0 && x0 > 0, p1 = in1 && x1 > 0;
+			cnt += (p0 ? 1 : 0) + (p1 ? 1 : 0);
+			if (p0 && n0 < mn) mn = n0;
+			if (p1 && n1 < mn) mn = n1;
+		}
 	}
 	// the reference breaks at the FIRST compatible constraint with normAbund <= minAbundance, whatever
 	// was counted before, and returns -2: "any" is enough
@@ -287,11 +369,20 @@ PSC_DEV double dp_scan_cover2(const DpState &st, uint64_t ta, uint64_t tb, int t
 		belowMin = true;
 		return -2;
 	}
-	if (!st.forAbundance && st.co.sum(ccnt) > 0) {
+	// both counts in one reduction when they cannot overflow their 15-bit fields
+	if (d.tcCnt < 32768) {
+		int both = st.co.sum((ccnt << 15) | cnt);
+		ccnt = both >> 15;
+		cnt = both & 32767;
+	} else {
+		ccnt = st.co.sum(ccnt);
+		cnt = st.co.sum(cnt);
+	}
+	// beta: smallest normAbund among the compatible constraints, depleted ones included
+	if (!st.forAbundance && ccnt > 0 && st.co.any(mnAll < beta)) {
 		mnAll = st.co.min_nonneg(mnAll);
 		if (mnAll < beta) beta = mnAll;
 	}
-	cnt = st.co.sum(cnt);
 	if (st.forAbundance) {
 		if (cnt > 0) {
 			mn = st.co.min_nonneg(mn);
@@ -329,9 +420,10 @@ PSC_DEV long long dp_memo_index(const DpState &st, const int *visit, int vcnt)
 // raising minAbundance only removes candidates or lowers their value, abundances do not change inside
 // an iteration, and the uncovered-edge rule is the same for every positive threshold -- so the winner
 // of the left fold (first maximum) is unchanged.  This saves most of the per-threshold recomputation.
-PSC_DEV bool dp_memo_hit(const DpState &st, const DpMemo *me, int strand)
+PSC_DEV bool dp_memo_hit(const DpState &st, long long mi, int strand)
 {
-	if (me->epoch != st.epoch || me->cover == -1 || me->strand != strand) return false;
+	const DpMemo *me = st.d.ent + mi;
+	if (st.d.eepoch[mi] != st.epoch || me->cover == -1 || me->strand != strand) return false;
 	if (me->timeStamp == st.timeStamp) return true;
 	if (me->minAbundance < st.minAbundance && me->cover == -2) return true;
 	return !st.forAbundance && me->mode == 0 && me->iter == st.iter && me->cover >= 0 && me->minAbundance > 0 &&
@@ -347,6 +439,27 @@ PSC_DEV void dp_sort_ext(const DpState &st, int *src, int extCnt, bool hasRoom)
 	const Coop &co = st.co;
 	const DpScratch &d = st.d;
 	if (extCnt <= 1) return;
+	if (co.n > 1 && extCnt <= co.n) {
+		// one element per lane: place the distinct keys in ascending order, ties by original position
+		bool have = co.lane < extCnt;
+		int x = have ? src[co.lane] : -1;
+		int key = have ? d.tcl[x] : 0x7fffffff;
+		int rank = 0, base = 0;
+		for (;;) {
+			int kv = co.min(key);
+			if (kv == 0x7fffffff) break;
+			uint32_t m = co.ballot(key == kv);
+			if (key == kv) {
+				rank = base + co.rank_in(m);
+				key = 0x7fffffff;
+			}
+			base += popc32(m);
+		}
+		co.sync();
+		if (have) src[rank] = x;
+		co.sync();
+		return;
+	}
 	int *tmp = src + extCnt;
 	if (hasRoom) {
 		int kmin = 0x7fffffff, kmax = -1;
@@ -463,9 +576,9 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 	st.minAbundance = 0;
 	for (int i = 0; i < n; ++i)
 		if (st.cs[i]) {
-			long long tq = clock64();
+			long long tq = st.prof ? clock64() : 0;
 			long long r = dp_solve_root(st, i);
-			st.cycRoot += clock64() - tq;
+			if (st.prof) st.cycRoot += clock64() - tq;
 			double c = d.ent[r].cover;
 			if (c > maxAbundance) maxAbundance = c;
 		}
@@ -485,8 +598,11 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 		for (;;) {
 			// cached result for this minAbundance? (.cpp:996-1000)
 			int hit = -1;
-			for (int k = 0; k < d.cCap; ++k)
-				if (d.cvalid[k] && d.ckey[k] == st.minAbundance) { hit = k; break; }
+			for (int k0 = 0; k0 < d.cCap && hit < 0; k0 += co.n) {
+				int k = k0 + co.lane;
+				uint32_t m = co.ballot(k < d.cCap && d.cvalid[k] && d.ckey[k] == st.minAbundance);
+				if (m) hit = k0 + ctz32(m);
+			}
 			if (hit >= 0) {
 				dp_take(st, maxCover, d.cbits + (long long)hit * W, d.cent[hit].cover, d.cent[hit].first, d.cent[hit].last);
 			} else {
@@ -495,16 +611,19 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 				++st.nLevels;
 				for (int i = 0; i < n; ++i) {
 					if (!st.cs[i]) continue;
-					long long tq = clock64();
+					long long tq = st.prof ? clock64() : 0;
 					long long r = dp_solve_root(st, i);
-					st.cycRoot += clock64() - tq;
+					if (st.prof) st.cycRoot += clock64() - tq;
 					double c = d.ent[r].cover;
 					if (c > maxCover.cover && c > 0) dp_take(st, maxCover, d.ebits + r * W, c, d.ent[r].first, d.ent[r].last);
 				}
 				if (maxCover.cover == -1) break;
 				int slot = -1;
-				for (int k = 0; k < d.cCap; ++k)
-					if (!d.cvalid[k]) { slot = k; break; }
+				for (int k0 = 0; k0 < d.cCap && slot < 0; k0 += co.n) {
+					int k = k0 + co.lane;
+					uint32_t m = co.ballot(k < d.cCap && !d.cvalid[k]);
+					if (m) slot = k0 + ctz32(m);
+				}
 				if (slot < 0) {
 					*st.err = 22;
 					slot = 0;
@@ -781,7 +900,7 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
                            char *txBase, int *n_tx_out, char *sm, size_t smBytes, long long *dbg)
 {
 	DpState st;
-	st.nStates = st.nLevels = st.nIters = st.nFrames = st.nRoots = st.cycRoot = st.cycAssign = st.sumExt = st.sumDrop = st.sumScan = 0;
+	st.nStates = st.nLevels = st.nIters = st.nFrames = st.nRoots = st.cycRoot = st.cycAssign = 0;
 	long long t0 = clock64();
 	st.co = co;
 	st.v = comp_view(g, u.comp);
@@ -792,6 +911,10 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 	int Ccap = t.C > 100 ? t.C : 100;
 	dp_scratch_layout(&st.d, scratchBase + u.scratch_off, v.n, E, Ccap, 1);
 	dp_use_shared(st.d, v.n, v.W, sm, smBytes);
+	{
+		long long nEnt = dp_memo_entries(v.n);
+		for (long long k = co.lane; k < nEnt; k += co.n) st.d.eepoch[k] = 0;
+	}
 	DpTxList out;
 	dp_txlist_layout(&out, txBase + u.tx_off, u.iterBound, v.W);
 	// the unit's transcript list is written straight into its persistent slot
@@ -803,6 +926,7 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 	st.ce = sv.can_end + v.base;
 	st.W = v.W;
 	st.epoch = 0;
+	st.prof = dbg != nullptr;
 	st.err = sv.error_flag;
 	st.forAbundance = false;
 	st.minAbundance = 0;
@@ -844,9 +968,6 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 	if (co.lane == 0) *n_tx_out = nt;
 	if (dbg && co.lane == 0) {
 		dbg[0] = clock64() - t0;
-		dbg[4] = st.sumExt;
-		dbg[5] = st.sumDrop;
-		dbg[6] = st.sumScan;
 		dbg[1] = st.nStates + ((st.cycRoot >> 20) << 32);
 		dbg[2] = st.nLevels + ((st.cycAssign >> 20) << 32);
 		dbg[3] = st.nIters + (st.nFrames << 12) + (st.nRoots << 40);

@@ -15,8 +15,8 @@
 //   * everything a nested key needs is derived incrementally from the walk: its bits are
 //     (child bits & ~owner key bits), its memo hash is the running hash, its count of uncovered
 //     edges a difference of two running counts;
-//   * SMALL (component of <= 128 subexons, W <= 2) keeps all bit vectors in registers and uses the
-//     loop-free compat2 / two-constraints-per-lane scans; wider components go through memory.
+//   * components of up to 256 subexons (W <= NW = 2 or 4 words) keep all bit vectors in registers and use the
+//     loop-free compat_r / two-constraints-per-lane scans; wider components (NW = 0) go through memory.
 // Depth-first order, strand rules and the strict '>' fold are the reference's, so results are
 // bit-identical (tests/: oracle parity on enumerate + DP sets).
 #pragma once
@@ -29,8 +29,10 @@ namespace pscdev {
 //            7 keyUncov 8 memo index 9 strand of the best path
 #define OWN(o, k) of[(o) * 10 + (k)]
 
-template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int start)
+template <int NW> PSC_DEVN long long dp_solve_root_t(DpState &stRef, int start)
 {
+	constexpr bool SMALL = NW > 0;
+	typedef BitsR<NW> BV;
 	// private copy: see the note in dp_pick about escaped addresses
 	DpState st = stRef;
 	const Coop co = st.co;
@@ -50,48 +52,38 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 	int extTop = 0;
 	int ok = -1; // top of the owner stack
 	long long ret = -1;
-	++st.nRoots;
+	int nStates = 0, nFrames = 0; // PSC_DEBUG_DP counters
 
 	// ---- the top owner ----
 	int o_vbase = 0, o_vcnt = 0, o_strand = 0, o_tcStart = 0, o_extBase = 0, o_extCnt = 0, o_keyUncov = 0, o_ei = 0;
 	int o_first = 0, o_last = 0;
 	long long o_mi = -1;
-	uint64_t o_ka = 0, o_kb = 0;         // key bits
+	BV o_k;                              // key bits
 	double o_cover = -1, o_beta = 1e300; // pdp
-	uint64_t o_pa = 0, o_pb = 0;
+	BV o_p;
 	int o_plast = 0, o_pstrand = 0;
 	// ---- the current position and the child being visited ----
 	int cp = 0, c_node = 0, c_strand = 0, c_ei = 0, c_ext = 0, c_uncov = 0;
 	uint32_t c_hash = 0;
-	uint64_t c_ba = 0, c_bb = 0;
+	BV c_b;
 	int np = 0, n_node = 0, n_strand = 0, n_ext = 0, n_uncov = 0;
 	uint32_t n_hash = 0;
-	uint64_t n_ba = 0, n_bb = 0;
+	BV n_b;
 	bool keepSearch = false;
 
 	// request: new owner with key P[nvbase .. nvbase+nvcnt)
 	int nvbase = 0, nvcnt = 1, nstrand = 0, ntcStart = 0, nfirst = start, nlast = start, nkeyUncov = 0;
 	uint32_t nhash = 0;
-	uint64_t nka = start < 64 ? (uint64_t)1 << start : 0, nkb = (start >= 64 && start < 128) ? (uint64_t)1 << (start - 64) : 0;
+	BV nk;
+	nk.clear();
+	nk.set(start);
 	int mode = 0; // 0 enter owner, 1 next child of (owner, cp), 2 evaluate child np, 4 owner done
 
 	co.sync();
 	if (co.lane == 0) P[0] = start;
 	co.sync();
 
-	long long tmark = clock64();
-	int lastMode = 0;
-#define PSC_DP_TICK(m)                                                                                          \
-	{                                                                                                           \
-		long long tn = clock64();                                                                               \
-		if (lastMode == 0) st.sumExt += tn - tmark;                                                             \
-		else if (lastMode == 1) st.sumDrop += tn - tmark;                                                       \
-		else st.sumScan += tn - tmark;                                                                          \
-		tmark = tn;                                                                                             \
-		lastMode = (m);                                                                                         \
-	}
 	for (;;) {
-		PSC_DP_TICK(mode == 0 ? 0 : (mode == 1 ? 1 : 2))
 		if (mode == 0) {
 			// =========== SolveSubTranscript(key) ===========
 			const int *key = P + nvbase;
@@ -103,13 +95,14 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			uint64_t *mbits = d.ebits + mi * W;
 			if (!SMALL) dp_build_sub(st, sub, nullptr, key, nvcnt, nullptr, 0);
 			bool hit = false;
-			if (dp_memo_hit(st, me, nstrand)) {
+			if (dp_memo_hit(st, mi, nstrand)) {
 				if (nvcnt <= 2) hit = true;
 				else if (me->cnt == nvcnt && me->first == nfirst) {
 					if (SMALL) {
-						uint64_t ra, rb;
-						range2(nfirst, nlast, ra, rb);
-						hit = (mbits[0] & ra) == nka && (W < 2 || (mbits[1] & rb) == nkb);
+						BV r, mb;
+						r.range(nfirst, nlast);
+						mb.load(mbits, W);
+						hit = mb.masked_equals(r, nk);
 					} else {
 						bool same = true;
 						for (int w = nfirst >> 6; w <= (nlast >> 6) && same; ++w)
@@ -124,7 +117,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				mode = 2;          // return into the owner
 				continue;
 			}
-			++st.nStates;
+			++nStates;
 			// ---- fresh evaluation: this key becomes the new top owner ----
 			if (ok >= 0) {
 				// park the owner below, its current position and the child that became the key's end
@@ -138,10 +131,8 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 					d.fdbeta[ok] = o_beta;
 					d.fdmeta[ok * 4 + 1] = o_plast;
 					if (SMALL) {
-						d.fdbits[(long long)ok * W] = o_pa;
-						if (W == 2) d.fdbits[(long long)ok * W + 1] = o_pb;
-						pbits[(long long)np * W] = n_ba;
-						if (W == 2) pbits[(long long)np * W + 1] = n_bb;
+						o_p.store(d.fdbits + (long long)ok * W, W);
+						n_b.store(pbits + (long long)np * W, W);
 					}
 					P[np] = n_node;
 					PPOS(np, 0) = n_strand;
@@ -158,8 +149,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			o_first = nfirst;
 			o_last = nlast;
 			o_keyUncov = nkeyUncov;
-			o_ka = nka;
-			o_kb = nkb;
+			o_k = nk;
 			{ // first constraint with first >= key[0]
 				int lo = o_first > 0 ? d.tcEnd[o_first - 1] : 0;
 				o_tcStart = lo > ntcStart ? lo : ntcStart;
@@ -167,7 +157,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			double cover = -1, beta0 = 1e300;
 			if (st.ce[o_last]) {
 				bool bm = false;
-				if (SMALL) cover = dp_scan_cover2(st, o_ka, o_kb, o_first, o_last, o_tcStart, o_last, 0, bm, beta0);
+				if (SMALL) cover = dp_scan_cover_r<NW>(st, o_k, o_first, o_last, o_tcStart, o_last, 0, bm, beta0);
 				else cover = dp_scan_cover(st, sub, o_first, o_last, o_tcStart, o_last, 0, bm, beta0);
 			}
 			// extensions: constraints whose head matches the tail of the partial path
@@ -180,10 +170,11 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 						int i0 = b0 + co.lane, i1 = i0 + co.n;
 						bool v0 = i0 < end, v1 = i1 < end;
 						int j0 = v0 ? i0 : end - 1, j1 = v1 ? i1 : end - 1;
-						uint64_t a0 = d.tcb[(long long)j0 * W], a1 = d.tcb[(long long)j1 * W];
-						uint64_t b0w = W == 2 ? d.tcb[(long long)j0 * W + 1] : 0, b1w = W == 2 ? d.tcb[(long long)j1 * W + 1] : 0;
-						bool is0 = v0 && compat2(o_ka, o_kb, o_first, o_last, true, a0, b0w, d.tcf[j0], d.tcl[j0]) == 2;
-						bool is1 = v1 && compat2(o_ka, o_kb, o_first, o_last, true, a1, b1w, d.tcf[j1], d.tcl[j1]) == 2;
+						BV x0, x1;
+						x0.load(d.tcb + (long long)j0 * W, W);
+						x1.load(d.tcb + (long long)j1 * W, W);
+						bool is0 = v0 && compat_r<NW>(o_k, o_first, o_last, true, x0, d.tcf[j0], d.tcl[j0]) == 2;
+						bool is1 = v1 && compat_r<NW>(o_k, o_first, o_last, true, x1, d.tcf[j1], d.tcl[j1]) == 2;
 						uint32_t m0 = co.ballot(is0);
 						if (is0) {
 							int p = o_extBase + o_extCnt + co.rank_in(m0);
@@ -220,14 +211,12 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			// pdp starts as the key itself
 			o_cover = cover;
 			o_beta = beta0;
-			o_pa = o_ka;
-			o_pb = o_kb;
+			o_p = o_k;
 			o_plast = o_last;
 			o_pstrand = o_strand;
 			if (co.lane == 0) {
 				if (SMALL) {
-					kbits[(long long)ok * W] = o_ka;
-					if (W == 2) kbits[(long long)ok * W + 1] = o_kb;
+					o_k.store(kbits + (long long)ok * W, W);
 				} else {
 					uint64_t *vb = d.fdbits + (long long)ok * W, *kb = kbits + (long long)ok * W;
 					for (int w = 0; w < W; ++w) { vb[w] = sub[w]; kb[w] = sub[w]; }
@@ -243,8 +232,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			c_ext = o_extCnt;
 			c_uncov = o_keyUncov;
 			c_hash = 0;
-			c_ba = o_ka;
-			c_bb = o_kb;
+			c_b = o_k;
 			mode = 1;
 			continue;
 		}
@@ -255,8 +243,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			co.sync();
 			if (co.lane == 0) {
 				if (SMALL) {
-					mbits[0] = o_pa;
-					if (W == 2) mbits[1] = o_pb;
+					o_p.store(mbits, W);
 				} else {
 					const uint64_t *vb = d.fdbits + (long long)ok * W;
 					for (int w = 0; w < W; ++w) mbits[w] = vb[w];
@@ -271,7 +258,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				me->cnt = o_vcnt;
 				me->minAbundance = st.minAbundance;
 				me->timeStamp = st.timeStamp;
-				me->epoch = st.epoch;
+				d.eepoch[o_mi] = st.epoch;
 			}
 			co.sync();
 			ret = o_mi;
@@ -289,10 +276,8 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			o_beta = d.fdbeta[ok];
 			o_plast = d.fdmeta[ok * 4 + 1];
 			if (SMALL) {
-				o_ka = kbits[(long long)ok * W];
-				o_kb = W == 2 ? kbits[(long long)ok * W + 1] : 0;
-				o_pa = d.fdbits[(long long)ok * W];
-				o_pb = W == 2 ? d.fdbits[(long long)ok * W + 1] : 0;
+				o_k.load(kbits + (long long)ok * W, W);
+				o_p.load(d.fdbits + (long long)ok * W, W);
 			}
 			np = keyEnd;
 			n_node = P[np];
@@ -300,19 +285,17 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			cp = np - 1;
 			if (cp == o_vbase + o_vcnt - 1) {
 				c_node = o_last; c_strand = o_strand; c_ei = o_ei; c_ext = o_extCnt; c_uncov = o_keyUncov; c_hash = 0;
-				c_ba = o_ka; c_bb = o_kb;
+				c_b = o_k;
 			} else {
 				c_node = P[cp];
 				c_strand = PPOS(cp, 0); c_ei = PPOS(cp, 1); c_ext = PPOS(cp, 2); c_uncov = PPOS(cp, 3); c_hash = (uint32_t)PPOS(cp, 4);
 				if (SMALL) {
-					c_ba = pbits[(long long)cp * W];
-					c_bb = W == 2 ? pbits[(long long)cp * W + 1] : 0;
+					c_b.load(pbits + (long long)cp * W, W);
 				}
 			}
 			keepSearch = false;
 			if (SMALL) {
-				n_ba = pbits[(long long)np * W];
-				n_bb = W == 2 ? pbits[(long long)np * W + 1] : 0;
+				n_b.load(pbits + (long long)np * W, W);
 			} else {
 				co.sync();
 				if (co.lane == 0)
@@ -348,19 +331,18 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				--cp;
 				if (cp == o_vbase + o_vcnt - 1) {
 					c_node = o_last; c_strand = o_strand; c_ei = o_ei; c_ext = o_extCnt; c_uncov = o_keyUncov; c_hash = 0;
-					c_ba = o_ka; c_bb = o_kb;
+					c_b = o_k;
 				} else {
 					c_node = P[cp];
 					c_strand = PPOS(cp, 0); c_ei = PPOS(cp, 1); c_ext = PPOS(cp, 2); c_uncov = PPOS(cp, 3); c_hash = (uint32_t)PPOS(cp, 4);
 					if (SMALL) {
-						c_ba = pbits[(long long)cp * W];
-						c_bb = W == 2 ? pbits[(long long)cp * W + 1] : 0;
+						c_b.load(pbits + (long long)cp * W, W);
 					}
 				}
 				continue;
 			}
 			// ---- visit child b at position np = cp + 1 (SearchSubTranscript entry, .cpp:385-422) ----
-			++st.nFrames;
+			++nFrames;
 			np = cp + 1;
 			n_node = b;
 			n_strand = ns;
@@ -368,8 +350,8 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			n_hash = (c_hash * nn + (uint32_t)b) % PSC_DP_HASH;
 			// path bits: (key | walk up to cp) | b
 			if (SMALL) {
-				n_ba = c_ba | (b < 64 ? (uint64_t)1 << b : 0);
-				n_bb = c_bb | (b >= 64 ? (uint64_t)1 << (b - 64) : 0);
+				n_b = c_b;
+				n_b.set(b);
 			} else {
 				const uint64_t *src = cp == o_vbase + o_vcnt - 1 ? kbits + (long long)ok * W : pbits + (long long)cp * W;
 				co.sync();
@@ -383,16 +365,19 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				co.sync();
 			}
 			// drop the pending extensions that no longer fit (.cpp:407-412)
+			int keptLast = 0; // .last of the furthest-reaching extension that stays pending
 			{
 				const int *ext = d.ext + o_extBase;
 				int i;
 				for (i = c_ext - 1; i >= 0; --i) {
 					int x = ext[i];
 					int xl = d.tcl[x];
+					keptLast = xl;
 					if (xl <= b) break;
 					if (SMALL) {
-						uint64_t xa = d.tcb[(long long)x * W], xb = W == 2 ? d.tcb[(long long)x * W + 1] : 0;
-						if ((((b < 64 ? xa : xb) >> (b & 63)) & 1) && compat2(n_ba, n_bb, o_first, b, true, xa, xb, d.tcf[x], xl) != 0) break;
+						BV xv;
+						xv.load(d.tcb + (long long)x * W, W);
+						if (xv.test(b) && compat_r<NW>(n_b, o_first, b, true, xv, d.tcf[x], xl) != 0) break;
 					} else {
 						if (bt_test(d.tcb + (long long)x * W, b) &&
 						    compat(cb, o_first, b, true, d.tcb + (long long)x * W, d.tcf[x], xl, W) != 0)
@@ -401,7 +386,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				}
 				n_ext = i + 1;
 			}
-			bool solveHere = v.noff[b + 1] > v.noff[b] && (n_ext == 0 || b >= d.tcl[d.ext[o_extBase + n_ext - 1]]);
+			bool solveHere = v.noff[b + 1] > v.noff[b] && (n_ext == 0 || b >= keptLast);
 			keepSearch = !solveHere;
 			ret = -1;
 			if (solveHere) {
@@ -413,8 +398,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				nfirst = nvcnt == 1 ? b : P[nvbase];
 				nhash = n_hash;
 				nkeyUncov = nvcnt == 1 ? 0 : n_uncov - PPOS(nvbase, 3);
-				nka = n_ba & ~o_ka;
-				nkb = n_bb & ~o_kb;
+				nk.and_not(n_b, o_k);
 				mode = 0; // answered by the memo (-> mode 2) or evaluated as a new owner (-> mode 4 -> 2)
 				continue;
 			}
@@ -438,10 +422,10 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 			if (vcover >= 0) {
 				double cover = vcover;
 				// parents | sub-solution
-				uint64_t sa = 0, sb = 0;
+				BV sv;
 				if (SMALL) {
-					sa = o_ka | vbits[0];
-					sb = W == 2 ? (o_kb | vbits[1]) : 0;
+					sv.load(vbits, W);
+					sv.or_with(o_k);
 				} else {
 					const uint64_t *kb = kbits + (long long)ok * W;
 					co.sync();
@@ -452,7 +436,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				if (!st.forAbundance && st.minAbundance > 0 && n_uncov > 0) belowMin = true;
 				bool bm2 = false;
 				double cbeta = vbeta;
-				if (SMALL) cover = dp_scan_cover2(st, sa, sb, o_first, vlast, o_tcStart, o_last, cover, bm2, cbeta);
+				if (SMALL) cover = dp_scan_cover_r<NW>(st, sv, o_first, vlast, o_tcStart, o_last, cover, bm2, cbeta);
 				else cover = dp_scan_cover(st, sub, o_first, vlast, o_tcStart, o_last, cover, bm2, cbeta);
 				if (bm2) belowMin = true;
 				bool takeBelow = belowMin && o_cover == -1;
@@ -462,8 +446,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 					o_plast = vlast;
 					o_pstrand = n_strand;
 					if (SMALL) {
-						o_pa = sa;
-						o_pb = sb;
+						o_p = sv;
 					} else {
 						co.sync();
 						if (co.lane == 0)
@@ -476,8 +459,8 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				o_plast = vlast;
 				o_pstrand = n_strand;
 				if (SMALL) {
-					o_pa = vbits[0] | o_ka;
-					o_pb = W == 2 ? (vbits[1] | o_kb) : 0;
+					o_p.load(vbits, W);
+					o_p.or_with(o_k);
 				} else {
 					co.sync();
 					if (co.lane == 0) {
@@ -497,7 +480,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				}
 				bool bm2 = false;
 				double cbeta = 1e300;
-				if (SMALL) cover = dp_scan_cover2(st, n_ba, n_bb, o_first, tag, o_tcStart, tag, cover, bm2, cbeta);
+				if (SMALL) cover = dp_scan_cover_r<NW>(st, n_b, o_first, tag, o_tcStart, tag, cover, bm2, cbeta);
 				else cover = dp_scan_cover(st, cb, o_first, tag, o_tcStart, tag, cover, bm2, cbeta);
 				if (bm2) below = true;
 				bool takeBelow = below && o_cover == -1;
@@ -507,8 +490,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 					o_plast = tag;
 					o_pstrand = n_strand;
 					if (SMALL) {
-						o_pa = n_ba;
-						o_pb = n_bb;
+						o_p = n_b;
 					} else {
 						co.sync();
 						if (co.lane == 0)
@@ -529,8 +511,7 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 					PPOS(np, 3) = n_uncov;
 					PPOS(np, 4) = (int)n_hash;
 					if (SMALL) {
-						pbits[(long long)np * W] = n_ba;
-						if (W == 2) pbits[(long long)np * W + 1] = n_bb;
+						n_b.store(pbits + (long long)np * W, W);
 					}
 				}
 				co.sync();
@@ -541,31 +522,26 @@ template <bool SMALL> PSC_DEV long long dp_solve_root_t(DpState &stRef, int star
 				c_ext = n_ext;
 				c_uncov = n_uncov;
 				c_hash = n_hash;
-				c_ba = n_ba;
-				c_bb = n_bb;
+				c_b = n_b;
 			}
 			ret = -1;
 			mode = 1;
 		}
 	}
 	co.sync();
-	PSC_DP_TICK(0)
-	stRef.sumExt = st.sumExt;
-	stRef.sumDrop = st.sumDrop;
-	stRef.sumScan = st.sumScan;
-	stRef.nStates = st.nStates;
-	stRef.nFrames = st.nFrames;
-	stRef.nRoots = st.nRoots;
+	stRef.nStates += nStates;
+	stRef.nFrames += nFrames;
+	++stRef.nRoots;
 	return ret;
 }
-#undef PSC_DP_TICK
 #undef PPOS
 #undef OWN
 
-PSC_DEVN long long dp_solve_root(DpState &st, int start)
+PSC_DEV long long dp_solve_root(DpState &st, int start)
 {
-	if (st.W <= 2) return dp_solve_root_t<true>(st, start);
-	return dp_solve_root_t<false>(st, start);
+	if (st.W <= 2) return dp_solve_root_t<2>(st, start);
+	if (st.W <= 4) return dp_solve_root_t<4>(st, start);
+	return dp_solve_root_t<0>(st, start);
 }
 
 } // namespace pscdev

@@ -3,6 +3,7 @@
 #include "../../include/psc.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>

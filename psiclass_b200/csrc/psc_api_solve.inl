@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(128) k_enumerate(GraphDev g, SolveDev sv, cons
 	}
 }
 
-__global__ void __launch_bounds__(128) k_dp_units(GraphDev g, SolveDev sv, const DpUnit *units, const int *order, int nUnits,
+#ifndef PSC_DP_MINBLOCKS
+#define PSC_DP_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, PSC_DP_MINBLOCKS) k_dp_units(GraphDev g, SolveDev sv, const DpUnit *units, const int *order, int nUnits,
                                                   char *scratch, char *txArena, int *n_tx, int *counter, int width, int smemPerWarp, long long *dbg)
 {
 	Coop co = make_coop(width);
@@ -133,6 +136,15 @@ int psc_solve(psc_ctx *ctx)
 	SolveState &st = ctx->solve;
 	const int S = ctx->prm.n_samples, nc = ctx->gd.n_comp, ns = ctx->gd.n_se;
 	long long launches = 0;
+	// PSC_DEBUG_HOST=1: wall-clock of the host-side sections (stderr)
+	const bool hostDbg = getenv("PSC_DEBUG_HOST") != nullptr;
+	auto hostT0 = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) {
+		if (!hostDbg) return;
+		auto t = std::chrono::steady_clock::now();
+		fprintf(stderr, "[host] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - hostT0).count());
+		hostT0 = t;
+	};
 	CK(cudaEventRecord(ctx->ev0, ctx->stream));
 	st.r_comp.clear(); st.r_sample.clear(); st.r_chr.clear(); st.r_gene.clear(); st.r_strand.clear();
 	st.r_exon_off.assign(1, 0); st.r_exon_start.clear(); st.r_exon_end.clear(); st.r_fpkm.clear(); st.r_cov.clear();
@@ -188,6 +200,7 @@ int psc_solve(psc_ctx *ctx)
 	CK(cudaMemcpyAsync(st.h_use_dp.data(), sv.use_dp, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 
+	lap("prologue");
 	// ---- candidate capacities ----
 	std::vector<long long> rowOff((size_t)nc + 1), bitsOff((size_t)nc + 1);
 	std::vector<int> enumList, dpList;
@@ -229,6 +242,7 @@ int psc_solve(psc_ctx *ctx)
 	sv.cand_sup1 = st.cand_sup1.as<int>();
 	sv.cand_sup2 = st.cand_sup2.as<int>();
 
+	lap("candidate capacities");
 	// ---- P2a: enumeration ----
 	if (!enumList.empty()) {
 		if (!upload(ctx, st.list, enumList.data(), enumList.size()) || !st.stk.ensure(sizeof(int) * 3 * ((size_t)ns + 1)))
@@ -245,6 +259,7 @@ int psc_solve(psc_ctx *ctx)
 		CK(cudaGetLastError());
 		CK(cudaStreamSynchronize(ctx->stream)); // enumList staging buffer is reused below
 	}
+	lap("enumerate");
 	// ---- P2b: DP.  Units are (component, sample); chunks of components that fit the memory budget ----
 	long long dpBytes = 0;
 	{
@@ -252,7 +267,6 @@ int psc_solve(psc_ctx *ctx)
 		while (i0 < dpList.size()) {
 			std::vector<DpUnit> units;
 			std::vector<long long> mergeOff, cost;
-			std::vector<std::pair<size_t, size_t>> zero; // (offset, bytes) memo regions
 			long long sAcc = 0, tAcc = 0, mAcc = 0;
 			size_t i1 = i0;
 			while (i1 < dpList.size()) {
@@ -291,7 +305,6 @@ int psc_solve(psc_ctx *ctx)
 					if (u.iterBound < 1) u.iterBound = 1;
 					u.scratch_off = sAcc + sNeed;
 					u.tx_off = tAcc + tNeed;
-					zero.push_back({(size_t)u.scratch_off, dp_scratch_zero_bytes(n)});
 					sNeed += (long long)dp_scratch_layout(nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100), 1);
 					tNeed += (long long)dp_txlist_layout(nullptr, nullptr, u.iterBound, W);
 					mine.push_back(u);
@@ -314,15 +327,14 @@ int psc_solve(psc_ctx *ctx)
 			std::vector<int> order((size_t)nUnits);
 			for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
 			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
-			for (size_t k = zero.size(); k > (size_t)nUnits; --k) zero.pop_back();
 			if (!st.scratch.ensure((size_t)std::max(sAcc, mAcc) + 16) || !st.dp_tx.ensure((size_t)tAcc + 16) ||
 			    !st.dp_ntx.ensure(sizeof(int) * (size_t)(nUnits + 1)))
 				return ctx->fail("out of device memory (DP scratch)");
-			for (auto &z : zero) CK(cudaMemsetAsync((char *)st.scratch.p + z.first, 0, z.second, ctx->stream));
 			CK(cudaMemsetAsync(st.dp_ntx.p, 0, sizeof(int) * (size_t)(nUnits + 1), ctx->stream));
 			if (!upload(ctx, st.list, dpList.data() + i0, (size_t)nComp) || !upload(ctx, st.dp_units, units.data(), units.size()) ||
 			    !upload(ctx, st.order, order.data(), order.size()) || !upload(ctx, st.scr_off, mergeOff.data(), mergeOff.size()))
 				return ctx->fail("out of device memory");
+			lap("dp host prep");
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
 			{
 				const int smemPerWarp = ctx->coop == 32 ? 16 * 1024 : 0; // 4 warps -> 64 KB per CTA, 3 CTAs per SM
@@ -353,6 +365,7 @@ int psc_solve(psc_ctx *ctx)
 			++launches;
 			CK(cudaGetLastError());
 			CK(cudaStreamSynchronize(ctx->stream));
+			lap("dp kernels");
 			if (getenv("PSC_DEBUG_DP")) {
 				std::vector<long long> h((size_t)nUnits * 8);
 				cudaMemcpy(h.data(), st.dp_dbg.p, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
@@ -369,10 +382,10 @@ int psc_solve(psc_ctx *ctx)
 				for (int k = 0; k < 12 && k < nUnits; ++k) {
 					int u = ix[(size_t)k];
 					int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
-					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld | Mcyc owner-entry %lld next-child %lld evaluate %lld\n", u, c, s,
+					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld\n", u, c, s,
 					        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
 					        h[(size_t)u * 8] / 1e6, h[(size_t)u * 8 + 1] & 0xffffffff, h[(size_t)u * 8 + 2] & 0xffffffff, h[(size_t)u * 8 + 3] & 0xfff, (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff, h[(size_t)u * 8 + 3] >> 40,
-					        h[(size_t)u * 8 + 1] >> 32, h[(size_t)u * 8 + 2] >> 32, h[(size_t)u * 8 + 4] >> 20, h[(size_t)u * 8 + 5] >> 20, h[(size_t)u * 8 + 6] >> 20);
+					        h[(size_t)u * 8 + 1] >> 32, h[(size_t)u * 8 + 2] >> 32);
 				}
 			}
 			i0 = i1;
@@ -423,6 +436,7 @@ int psc_solve(psc_ctx *ctx)
 		     upload(ctx, st.order, order.data(), order.size()) && st.n_pred.ensure(sizeof(int) * (size_t)nUnits) &&
 		     st.n_raw.ensure(sizeof(int) * (size_t)nUnits) && st.n_exon.ensure(sizeof(int) * (size_t)nUnits);
 		if (!ok) return ctx->fail("out of device memory (unit scratch)");
+		lap("units host prep");
 		ChunkDev ch;
 		ch.c0 = c0;
 		ch.c1 = c1;
@@ -446,6 +460,7 @@ int psc_solve(psc_ctx *ctx)
 		CK(cudaMemcpyAsync(hPred.data(), ch.n_pred, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaMemcpyAsync(hExon.data(), ch.n_exon, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
+		lap("units kernels");
 		std::vector<long long> txOff((size_t)nUnits + 1), exOff((size_t)nUnits + 1);
 		long long nt = 0, ne = 0;
 		for (int u = 0; u < nUnits; ++u) {
@@ -475,6 +490,7 @@ int psc_solve(psc_ctx *ctx)
 			o.exon_end = st.o_exon_end.as<int>();
 			o.fpkm = st.o_fpkm.as<double>();
 			o.cov = st.o_cov.as<double>();
+			lap("emit host prep");
 			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
 			KLAUNCH(6, k_emit, launch_grid(ctx, nUnits), 128, ctx->gd, sv, ch, o, st.tx_off.as<long long>(), st.ex_off.as<long long>(),
 			        counter, ctx->coop);
@@ -496,12 +512,14 @@ int psc_solve(psc_ctx *ctx)
 			CK(cudaMemcpyAsync(st.r_exon_start.data() + e0, o.exon_start, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
 			CK(cudaMemcpyAsync(st.r_exon_end.data() + e0, o.exon_end, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
 			CK(cudaStreamSynchronize(ctx->stream));
+			lap("emit + copy back");
 			st.r_exon_off.pop_back();
 			for (long long k = 0; k < nt; ++k) st.r_exon_off.push_back((long long)e0 + eo[(size_t)k]);
 			st.r_exon_off.push_back((long long)e0 + ne);
 		}
 		c0 = c1;
 	}
+	lap("exon offsets");
 	int herr = 0;
 	CK(cudaMemcpyAsync(&herr, sv.error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaEventRecord(ctx->ev1, ctx->stream));

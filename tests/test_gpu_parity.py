@@ -20,6 +20,9 @@ CONFIGS = [
     dict(seed=47, n_genes=30, n_samples=3, mean_pairs=0.3, exon_min=1, exon_max=2),
     # ~146 subexons per component: three 64-bit words per bit vector, DP path, int32 path-count overflow (Q4)
     dict(seed=20, n_genes=4, n_samples=3, exon_mu=4.8, exon_sigma=0.1, exon_min=110, exon_max=120, iso_lambda=2.0, p_alt=0.3, mean_pairs=150.0),
+    # four words (still the register-resident DP walk) and five words (the generic in-memory walk)
+    dict(seed=21, n_genes=3, n_samples=2, exon_mu=5.3, exon_sigma=0.1, exon_min=180, exon_max=200, iso_lambda=2.0, p_alt=0.3, mean_pairs=150.0),
+    dict(seed=22, n_genes=2, n_samples=2, exon_mu=5.6, exon_sigma=0.1, exon_min=230, exon_max=260, iso_lambda=2.0, p_alt=0.3, mean_pairs=150.0),
 ]
 
 
