@@ -69,11 +69,15 @@ PSC_DEV void abundance_em(const Coop &co, const CompView &v, const TableView &t,
 		for (int i = co.lane; i < T; i += co.n) {
 			const uint64_t *bt = sc.ebtable + (long long)i * MW;
 			double newAbund = 0, r = sc.rho[i];
-			for (int j = 0; j < M; ++j)
-				if (bt_test(bt, j)) {
+			for (int w = 0; w < MW; ++w) { // compatible pairs only, still in index order
+				uint64_t word = bt[w];
+				while (word) {
+					int j = w * 64 + ctz64(word);
+					word &= word - 1;
 					double factor = t.pec[j];
 					newAbund += (r / sc.sumj[j]) * t.psup[j] * factor;
 				}
+			}
 			pv.pr.abundance[i] = newAbund; // value of the final loop survives (.cpp:2227-2234)
 			double nr = newAbund / sc.tlen[i];
 			if (pv.pr.corr[i] == -1 && nr > 0.1 / (double)prm.readLen) nr = 0.1 / (double)prm.readLen;

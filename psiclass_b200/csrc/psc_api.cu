@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "psc_internal.h"
@@ -115,6 +116,7 @@ struct SampleState {
 struct psc_ctx {
 	int device = 0;
 	cudaStream_t stream = 0;
+	cudaStream_t stream2 = 0; // per-unit kernels of the enumerated components, running under the DP kernel's tail
 	cudaEvent_t ev0 = 0, ev1 = 0;
 	std::string err;
 	psc_params prm;
@@ -142,19 +144,21 @@ struct psc_ctx {
 	std::vector<cudaEvent_t> evPool;
 	std::vector<int> evIds;
 	size_t evUsed = 0;
-	void ktime_begin(int id)
+	cudaStream_t evStream = 0;
+	void ktime_begin(int id, cudaStream_t on = nullptr)
 	{
+		evStream = on ? on : stream;
 		if (evUsed + 2 > evPool.size()) {
 			evPool.resize(evUsed + 2);
 			cudaEventCreate(&evPool[evUsed]);
 			cudaEventCreate(&evPool[evUsed + 1]);
 		}
 		evIds.push_back(id);
-		cudaEventRecord(evPool[evUsed], stream);
+		cudaEventRecord(evPool[evUsed], evStream);
 	}
 	void ktime_end()
 	{
-		cudaEventRecord(evPool[evUsed + 1], stream);
+		cudaEventRecord(evPool[evUsed + 1], evStream);
 		evUsed += 2;
 	}
 	void ktime_collect() // call after a stream synchronisation
@@ -182,16 +186,23 @@ struct psc_ctx {
 		ctx->ktime_end();                                            \
 	} while (0)
 
+#define KLAUNCH_ON(strm, id, kernel, grid, block, ...)             \
+	do {                                                            \
+		ctx->ktime_begin(id, strm);                                  \
+		PSC_LAUNCH(kernel, grid, block, strm, __VA_ARGS__);          \
+		ctx->ktime_end();                                            \
+	} while (0)
+
 #define CK(call)                                                                                   \
 	do {                                                                                            \
 		cudaError_t e_ = (call);                                                                     \
 		if (e_ != cudaSuccess) return ctx->fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
 	} while (0)
 
-template <class T> static bool upload(psc_ctx *ctx, DevBuf &b, const T *src, size_t n)
+template <class T> static bool upload(psc_ctx *ctx, DevBuf &b, const T *src, size_t n, cudaStream_t on = nullptr)
 {
 	if (!b.ensure(n * sizeof(T))) return false;
-	if (n) return cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+	if (n) return cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, on ? on : ctx->stream) == cudaSuccess;
 	return true;
 }
 
@@ -210,8 +221,9 @@ int psc_create(psc_ctx **out, int device)
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
 	size_t fr = 0, tot = 0;
-	if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ctx->mem_budget = fr / 3;
-	if (cudaStreamCreate(&ctx->stream) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+	if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ctx->mem_budget = fr / 4;
+	if (cudaStreamCreate(&ctx->stream) != cudaSuccess || cudaStreamCreate(&ctx->stream2) != cudaSuccess ||
+	    cudaEventCreate(&ctx->ev0) != cudaSuccess ||
 	    cudaEventCreate(&ctx->ev1) != cudaSuccess) {
 		delete ctx;
 		return 5;
@@ -239,6 +251,7 @@ void psc_destroy(psc_ctx *ctx)
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	cudaStreamDestroy(ctx->stream);
+	cudaStreamDestroy(ctx->stream2);
 	delete ctx;
 }
 

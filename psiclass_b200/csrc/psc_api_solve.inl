@@ -79,19 +79,19 @@ __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const
 	}
 }
 
-// phase: 1 pick round 1, 2 pick round 2 + filtration, 3 rescue
-__global__ void __launch_bounds__(128, 4) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *order, int *counter,
-                                               int width)
+// phase: 1 pick round 1, 2 pick round 2 + filtration, 3 rescue.  list[0 .. nList): the chunk-local units of this pass,
+// heaviest first
+__global__ void __launch_bounds__(128, 4) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *list, int nList,
+                                               int *counter, int width)
 {
 	Coop co = make_coop(width);
 	int S = sv.prm.S;
-	int nUnits = (ch.c1 - ch.c0) * S;
 	for (;;) {
 		int u = 0;
 		if (co.lane == 0) u = atomic_add(counter, 1);
 		u = co.bcast(u, 0);
-		if (u >= nUnits) break;
-		int ul = order ? order[u] : u;
+		if (u >= nList) break;
+		int ul = list[u];
 		int c = ch.c0 + ul / S, s = ul % S;
 		if (phase == 1) unit_pick_round1(co, g, sv, ch, c, s);
 		else if (phase == 2) unit_pick_round2(co, g, sv, ch, c, s);
@@ -101,20 +101,62 @@ __global__ void __launch_bounds__(128, 4) k_units(GraphDev g, SolveDev sv, Chunk
 }
 
 __global__ void __launch_bounds__(128) k_emit(GraphDev g, SolveDev sv, ChunkDev ch, OutDev o, const long long *tx_off,
-                                              const long long *ex_off, int *counter, int width)
+                                              const long long *ex_off, const int *list, int nList, int *counter, int width)
 {
 	Coop co = make_coop(width);
 	int S = sv.prm.S;
-	int nUnits = (ch.c1 - ch.c0) * S;
 	for (;;) {
 		int u = 0;
 		if (co.lane == 0) u = atomic_add(counter, 1);
 		u = co.bcast(u, 0);
-		if (u >= nUnits) break;
-		int c = ch.c0 + u / S, s = u % S;
-		unit_emit(co, g, sv, ch, c, s, o, tx_off[u], ex_off[u]);
+		if (u >= nList) break;
+		int ul = list[u];
+		int c = ch.c0 + ul / S, s = ul % S;
+		unit_emit(co, g, sv, ch, c, s, o, tx_off[ul], ex_off[ul]);
 		co.sync();
 	}
+}
+
+// psc_solve may run the per-unit kernels in two passes (enumerated components, then DP components); each pass
+// appends its transcripts in component order.  Restore the single component-major order the C ABI promises.
+static void merge_passes(SolveState &st, size_t nA)
+{
+	const size_t nt = st.r_comp.size();
+	if (nA == 0 || nA == nt) return;
+	std::vector<size_t> perm(nt);
+	{
+		size_t a = 0, b = nA, k = 0;
+		while (a < nA && b < nt) perm[k++] = st.r_comp[a] < st.r_comp[b] ? a++ : b++;
+		while (a < nA) perm[k++] = a++;
+		while (b < nt) perm[k++] = b++;
+	}
+	auto gather = [&](auto &vec) {
+		typename std::remove_reference<decltype(vec)>::type out(vec.size());
+		for (size_t k = 0; k < nt; ++k) out[k] = vec[perm[k]];
+		vec.swap(out);
+	};
+	std::vector<long long> off(nt + 1);
+	std::vector<int> es(st.r_exon_start.size()), ee(st.r_exon_end.size());
+	long long e = 0;
+	for (size_t k = 0; k < nt; ++k) {
+		long long s0 = st.r_exon_off[perm[k]], s1 = st.r_exon_off[perm[k] + 1];
+		off[k] = e;
+		for (long long q = s0; q < s1; ++q, ++e) {
+			es[(size_t)e] = st.r_exon_start[(size_t)q];
+			ee[(size_t)e] = st.r_exon_end[(size_t)q];
+		}
+	}
+	off[nt] = e;
+	st.r_exon_off.swap(off);
+	st.r_exon_start.swap(es);
+	st.r_exon_end.swap(ee);
+	gather(st.r_comp);
+	gather(st.r_sample);
+	gather(st.r_chr);
+	gather(st.r_gene);
+	gather(st.r_strand);
+	gather(st.r_fpkm);
+	gather(st.r_cov);
 }
 
 static int launch_grid(psc_ctx *ctx, long long units)
@@ -259,266 +301,328 @@ int psc_solve(psc_ctx *ctx)
 		CK(cudaGetLastError());
 		CK(cudaStreamSynchronize(ctx->stream)); // enumList staging buffer is reused below
 	}
+	CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	// ---- P3..P6 per chunk of components, as a pass over all components (pass 0), over all but the heavy DP
+	// components (1) or over the heavy DP components (2).  Pass 1 runs on the second stream with its own buffers
+	// while the heavy DP units are still busy on the main one. ----
+	std::vector<char> group((size_t)nc, 0); // 2: heavy DP component
+	auto run_units = [&](int pass, cudaStream_t strm, UnitBufs &ub, int *cnt) -> int {
+		int c0 = 0;
+		while (c0 < nc) {
+			std::vector<long long> scrOff, predOff;
+			std::vector<long long> cost;
+			std::vector<int> order; // chunk-local ids of the units of this pass
+			long long sAcc = 0, pAcc = 0;
+			int c1 = c0;
+			while (c1 < nc) {
+				int n = ctx->h_comp_off[(size_t)c1 + 1] - ctx->h_comp_off[(size_t)c1];
+				int A = st.h_n_cand[(size_t)c1];
+				long long sNeed = 0, pNeed = 0;
+				std::vector<long long> so((size_t)S), po((size_t)S);
+				const bool mine = pass == 0 || (group[(size_t)c1] == 2) == (pass == 2);
+				for (int s = 0; s < S && mine; ++s) {
+					int M = ctx->samples[(size_t)s].h_npair[(size_t)c1], C = ctx->samples[(size_t)s].h_ncon[(size_t)c1];
+					int cap = std::max(1, std::min(A, M + 1));
+					so[(size_t)s] = sNeed;
+					po[(size_t)s] = pNeed;
+					sNeed += (long long)unit_scratch_layout(nullptr, nullptr, A, M, cap, n, C, ctx->h_comp_ng[(size_t)c1], ctx->h_next_cnt[(size_t)c1]);
+					pNeed += (long long)unit_pred_layout(nullptr, nullptr, cap);
+				}
+				if (c1 > c0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
+				for (int s = 0; s < S; ++s) {
+					scrOff.push_back(sAcc + so[(size_t)s]);
+					predOff.push_back(pAcc + po[(size_t)s]);
+					int M = ctx->samples[(size_t)s].h_npair[(size_t)c1];
+					cost.push_back((long long)A * (M + 1));
+					if (mine) order.push_back((c1 - c0) * S + s);
+				}
+				sAcc += sNeed;
+				pAcc += pNeed;
+				++c1;
+			}
+			scrOff.push_back(sAcc);
+			predOff.push_back(pAcc);
+			int nUnits = (c1 - c0) * S;
+			int nList = (int)order.size();
+			if (nList == 0) {
+				c0 = c1;
+				continue;
+			}
+			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+			ok = ub.scratch.ensure((size_t)sAcc + 16) && ub.pred.ensure((size_t)pAcc + 16) &&
+			     upload(ctx, ub.scr_off, scrOff.data(), scrOff.size(), strm) && upload(ctx, ub.pred_off, predOff.data(), predOff.size(), strm) &&
+			     upload(ctx, ub.order, order.data(), order.size(), strm) && ub.n_pred.ensure(sizeof(int) * (size_t)nUnits) &&
+			     ub.n_raw.ensure(sizeof(int) * (size_t)nUnits) && ub.n_exon.ensure(sizeof(int) * (size_t)nUnits);
+			if (!ok) return ctx->fail("out of device memory (unit scratch)");
+			lap("units host prep");
+			ChunkDev ch;
+			ch.c0 = c0;
+			ch.c1 = c1;
+			ch.scratch_off = ub.scr_off.as<long long>();
+			ch.scratch = (char *)ub.scratch.p;
+			ch.pred_off = ub.pred_off.as<long long>();
+			ch.pred = (char *)ub.pred.p;
+			ch.n_pred = ub.n_pred.as<int>();
+			ch.n_raw = ub.n_raw.as<int>();
+			ch.n_exon = ub.n_exon.as<int>();
+			CK(cudaMemsetAsync(ch.n_pred, 0, sizeof(int) * (size_t)nUnits, strm));
+			CK(cudaMemsetAsync(ch.n_raw, 0, sizeof(int) * (size_t)nUnits, strm));
+			CK(cudaMemsetAsync(ch.n_exon, 0, sizeof(int) * (size_t)nUnits, strm));
+			for (int phase = 1; phase <= 3; ++phase) {
+				CK(cudaMemsetAsync(cnt, 0, 32, strm));
+				KLAUNCH_ON(strm, phase == 1 ? 5 : (phase == 2 ? 8 : 9), k_units, launch_grid(ctx, nList), 128, ctx->gd, sv, ch, phase, ub.order.as<int>(), nList, cnt, ctx->coop);
+				++launches;
+				CK(cudaGetLastError());
+				if (hostDbg) {
+					CK(cudaStreamSynchronize(strm));
+					lap(phase == 1 ? "  units phase 1 (pick)" : (phase == 2 ? "  units phase 2 (pick, refine, EM)" : "  units phase 3 (rescue)"));
+				}
+			}
+			std::vector<int> hPred((size_t)nUnits), hExon((size_t)nUnits);
+			CK(cudaMemcpyAsync(hPred.data(), ch.n_pred, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost, strm));
+			CK(cudaMemcpyAsync(hExon.data(), ch.n_exon, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost, strm));
+			CK(cudaStreamSynchronize(strm));
+			lap("units kernels");
+			std::vector<long long> txOff((size_t)nUnits + 1), exOff((size_t)nUnits + 1);
+			long long nt = 0, ne = 0;
+			for (int u = 0; u < nUnits; ++u) {
+				txOff[(size_t)u] = nt;
+				exOff[(size_t)u] = ne;
+				nt += hPred[(size_t)u];
+				ne += hExon[(size_t)u];
+			}
+			txOff[(size_t)nUnits] = nt;
+			exOff[(size_t)nUnits] = ne;
+			if (nt > 0) {
+				ok = upload(ctx, ub.tx_off, txOff.data(), txOff.size(), strm) && upload(ctx, ub.ex_off, exOff.data(), exOff.size(), strm) &&
+				     ub.o_comp.ensure(sizeof(int) * (size_t)nt) && ub.o_sample.ensure(sizeof(int) * (size_t)nt) &&
+				     ub.o_chr.ensure(sizeof(int) * (size_t)nt) && ub.o_gene.ensure(sizeof(int) * (size_t)nt) &&
+				     ub.o_strand.ensure((size_t)nt) && ub.o_exon_off.ensure(sizeof(long long) * (size_t)nt) &&
+				     ub.o_exon_start.ensure(sizeof(int) * (size_t)(ne + 1)) && ub.o_exon_end.ensure(sizeof(int) * (size_t)(ne + 1)) &&
+				     ub.o_fpkm.ensure(sizeof(double) * (size_t)nt) && ub.o_cov.ensure(sizeof(double) * (size_t)nt);
+				if (!ok) return ctx->fail("out of device memory (output)");
+				OutDev o;
+				o.comp = ub.o_comp.as<int>();
+				o.sample = ub.o_sample.as<int>();
+				o.chr = ub.o_chr.as<int>();
+				o.gene = ub.o_gene.as<int>();
+				o.strand = ub.o_strand.as<int8_t>();
+				o.exon_off = ub.o_exon_off.as<long long>();
+				o.exon_start = ub.o_exon_start.as<int>();
+				o.exon_end = ub.o_exon_end.as<int>();
+				o.fpkm = ub.o_fpkm.as<double>();
+				o.cov = ub.o_cov.as<double>();
+				lap("emit host prep");
+				CK(cudaMemsetAsync(cnt, 0, 32, strm));
+				KLAUNCH_ON(strm, 6, k_emit, launch_grid(ctx, nList), 128, ctx->gd, sv, ch, o, ub.tx_off.as<long long>(), ub.ex_off.as<long long>(),
+				           ub.order.as<int>(), nList, cnt, ctx->coop);
+				++launches;
+				CK(cudaGetLastError());
+				size_t t0 = st.r_comp.size(), e0 = st.r_exon_start.size();
+				st.r_comp.resize(t0 + (size_t)nt); st.r_sample.resize(t0 + (size_t)nt); st.r_chr.resize(t0 + (size_t)nt);
+				st.r_gene.resize(t0 + (size_t)nt); st.r_strand.resize(t0 + (size_t)nt); st.r_fpkm.resize(t0 + (size_t)nt);
+				st.r_cov.resize(t0 + (size_t)nt); st.r_exon_start.resize(e0 + (size_t)ne); st.r_exon_end.resize(e0 + (size_t)ne);
+				std::vector<long long> eo((size_t)nt);
+				CK(cudaMemcpyAsync(st.r_comp.data() + t0, o.comp, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(st.r_sample.data() + t0, o.sample, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(st.r_chr.data() + t0, o.chr, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(st.r_gene.data() + t0, o.gene, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(st.r_strand.data() + t0, o.strand, (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(st.r_fpkm.data() + t0, o.fpkm, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(st.r_cov.data() + t0, o.cov, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(eo.data(), o.exon_off, sizeof(long long) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(st.r_exon_start.data() + e0, o.exon_start, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(st.r_exon_end.data() + e0, o.exon_end, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, strm));
+				CK(cudaStreamSynchronize(strm));
+				lap("emit + copy back");
+				st.r_exon_off.pop_back();
+				for (long long k = 0; k < nt; ++k) st.r_exon_off.push_back((long long)e0 + eo[(size_t)k]);
+				st.r_exon_off.push_back((long long)e0 + ne);
+			}
+			c0 = c1;
+		}
+		return 0;
+	};
 	lap("enumerate");
 	// ---- P2b: DP.  Units are (component, sample); chunks of components that fit the memory budget ----
 	long long dpBytes = 0;
-	{
-		size_t i0 = 0;
-		while (i0 < dpList.size()) {
-			std::vector<DpUnit> units;
-			std::vector<long long> mergeOff, cost;
-			long long sAcc = 0, tAcc = 0, mAcc = 0;
-			size_t i1 = i0;
-			while (i1 < dpList.size()) {
-				int c = dpList[i1];
-				int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
-				int W = (n + 63) / 64;
-				long long cap = rowOff[(size_t)c + 1] - rowOff[(size_t)c];
-				// the reference visits the samples in descending number of constraints (qsort ascending,
-				// stable, walked from the back: Q11)
-				std::vector<int> ord((size_t)S);
-				for (int s = 0; s < S; ++s) ord[(size_t)s] = s;
-				std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-					return ctx->samples[(size_t)a].h_ncon[(size_t)c] < ctx->samples[(size_t)b].h_ncon[(size_t)c];
-				});
-				std::vector<DpUnit> mine;
-				long long sNeed = 0, tNeed = 0;
-				int downsampleCnt = -1;
-				for (int oi = S - 1; oi >= 0; --oi) {
-					int s = ord[(size_t)oi];
-					int C = ctx->samples[(size_t)s].h_ncon[(size_t)c], M = ctx->samples[(size_t)s].h_npair[(size_t)c];
-					DpUnit u;
-					u.comp = c;
-					u.sample = s;
-					u.iterBound = oi == S - 1 ? C : 100;
-					u.stride = 0;
-					if (ctx->prm.max_dp_constraint_size <= 0) {
-						bool down = (C > 1000 && (long long)C * 10 < M) || (downsampleCnt > 0 && C >= downsampleCnt) || n >= 1500;
-						if (down) { // TranscriptDecider.cpp:3214-3227
-							int stride = C > 0 ? M / C : 1;
-							if (downsampleCnt > 0) stride = C / downsampleCnt;
-							if (stride < 1) stride = 1;
-							u.stride = stride;
-							if (downsampleCnt <= 0) downsampleCnt = (C + stride - 1) / stride;
+	auto run_dp = [&](const std::vector<int> &comps, cudaStream_t strm, DpBufs &db, int *cnt, bool wait) -> int {
+			size_t i0 = 0;
+			while (i0 < comps.size()) {
+				std::vector<DpUnit> units;
+				std::vector<long long> mergeOff, cost;
+				long long sAcc = 0, tAcc = 0, mAcc = 0;
+				size_t i1 = i0;
+				while (i1 < comps.size()) {
+					int c = comps[i1];
+					int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
+					int W = (n + 63) / 64;
+					long long cap = rowOff[(size_t)c + 1] - rowOff[(size_t)c];
+					// the reference visits the samples in descending number of constraints (qsort ascending,
+					// stable, walked from the back: Q11)
+					std::vector<int> ord((size_t)S);
+					for (int s = 0; s < S; ++s) ord[(size_t)s] = s;
+					std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+						return ctx->samples[(size_t)a].h_ncon[(size_t)c] < ctx->samples[(size_t)b].h_ncon[(size_t)c];
+					});
+					std::vector<DpUnit> mine;
+					long long sNeed = 0, tNeed = 0;
+					int downsampleCnt = -1;
+					for (int oi = S - 1; oi >= 0; --oi) {
+						int s = ord[(size_t)oi];
+						int C = ctx->samples[(size_t)s].h_ncon[(size_t)c], M = ctx->samples[(size_t)s].h_npair[(size_t)c];
+						DpUnit u;
+						u.comp = c;
+						u.sample = s;
+						u.iterBound = oi == S - 1 ? C : 100;
+						u.stride = 0;
+						if (ctx->prm.max_dp_constraint_size <= 0) {
+							bool down = (C > 1000 && (long long)C * 10 < M) || (downsampleCnt > 0 && C >= downsampleCnt) || n >= 1500;
+							if (down) { // TranscriptDecider.cpp:3214-3227
+								int stride = C > 0 ? M / C : 1;
+								if (downsampleCnt > 0) stride = C / downsampleCnt;
+								if (stride < 1) stride = 1;
+								u.stride = stride;
+								if (downsampleCnt <= 0) downsampleCnt = (C + stride - 1) / stride;
+							}
 						}
+						if (u.iterBound < 1) u.iterBound = 1;
+						u.scratch_off = sAcc + sNeed;
+						u.tx_off = tAcc + tNeed;
+						sNeed += (long long)dp_scratch_layout(nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100), 1);
+						tNeed += (long long)dp_txlist_layout(nullptr, nullptr, u.iterBound, W);
+						mine.push_back(u);
 					}
-					if (u.iterBound < 1) u.iterBound = 1;
-					u.scratch_off = sAcc + sNeed;
-					u.tx_off = tAcc + tNeed;
-					sNeed += (long long)dp_scratch_layout(nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100), 1);
-					tNeed += (long long)dp_txlist_layout(nullptr, nullptr, u.iterBound, W);
-					mine.push_back(u);
+					if (i1 > i0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
+					for (auto &u : mine) {
+						// algorithmic bytes of the DP kernel: the sample's constraint table read once, its transcript list written once
+						dpBytes += (long long)ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] * (8LL * W + 40) + (long long)u.iterBound * (8LL * W + 8);
+						units.push_back(u);
+						cost.push_back((long long)u.iterBound * (ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] + 1));
+					}
+					sAcc += sNeed;
+					tAcc += tNeed;
+					mergeOff.push_back(mAcc);
+					mAcc += (long long)dp_merge_layout(nullptr, nullptr, W, cap);
+					++i1;
 				}
-				if (i1 > i0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
-				for (auto &u : mine) {
-					// algorithmic bytes of the DP kernel: the sample's constraint table read once, its transcript list written once
-					dpBytes += (long long)ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] * (8LL * W + 40) + (long long)u.iterBound * (8LL * W + 8);
-					units.push_back(u);
-					cost.push_back((long long)u.iterBound * (ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] + 1));
+				// note: the offsets of the units we rolled back (mine, on break) were never committed
+				int nUnits = (int)units.size(), nComp = (int)(i1 - i0);
+				std::vector<int> order((size_t)nUnits);
+				for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
+				std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+				if (!(*db.scratch).ensure((size_t)std::max(sAcc, mAcc) + 16) || !db.dp_tx.ensure((size_t)tAcc + 16) ||
+				    !db.dp_ntx.ensure(sizeof(int) * (size_t)(nUnits + 1)))
+					return ctx->fail("out of device memory (DP scratch)");
+				CK(cudaMemsetAsync(db.dp_ntx.p, 0, sizeof(int) * (size_t)(nUnits + 1), strm));
+				if (!upload(ctx, db.list, comps.data() + i0, (size_t)nComp, strm) || !upload(ctx, db.dp_units, units.data(), units.size(), strm) ||
+				    !upload(ctx, db.dp_order, order.data(), order.size(), strm) || !upload(ctx, db.dp_scr_off, mergeOff.data(), mergeOff.size(), strm))
+					return ctx->fail("out of device memory");
+				lap("dp host prep");
+				CK(cudaMemsetAsync(cnt, 0, 32, strm));
+				{
+					const int smemPerWarp = ctx->coop == 32 ? 16 * 1024 : 0; // 4 warps -> 64 KB per CTA, 3 CTAs per SM
+					long long *dbgPtr = nullptr;
+					const bool dbgOn = getenv("PSC_DEBUG_DP") != nullptr;
+					if (dbgOn) {
+						if (!st.dp_dbg.ensure(sizeof(long long) * 8 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
+						CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 8 * (size_t)(nUnits + 1), strm));
+						dbgPtr = st.dp_dbg.as<long long>();
+					}
+	#ifndef PSC_CPU_SHIM
+					CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16 * 1024));
+					ctx->ktime_begin(4, strm);
+					k_dp_units<<<launch_grid(ctx, nUnits), 128, 4 * smemPerWarp, strm>>>(
+					    ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits, (char *)(*db.scratch).p, (char *)db.dp_tx.p,
+					    db.dp_ntx.as<int>(), cnt, ctx->coop, smemPerWarp, dbgPtr);
+					ctx->ktime_end();
+	#else
+					KLAUNCH_ON(strm, 4, k_dp_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits,
+					        (char *)(*db.scratch).p, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, ctx->coop, smemPerWarp, dbgPtr);
+	#endif
 				}
-				sAcc += sNeed;
-				tAcc += tNeed;
-				mergeOff.push_back(mAcc);
-				mAcc += (long long)dp_merge_layout(nullptr, nullptr, W, cap);
-				++i1;
+				++launches;
+				CK(cudaGetLastError());
+				CK(cudaMemsetAsync(cnt, 0, 32, strm));
+				KLAUNCH_ON(strm, 7, k_dp_merge, launch_grid(ctx, nComp), 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.list.as<int>(), nComp,
+				        db.dp_ntx.as<int>(), (const char *)db.dp_tx.p, (char *)(*db.scratch).p, db.dp_scr_off.as<long long>(), cnt, ctx->coop);
+				++launches;
+				CK(cudaGetLastError());
+				if (!wait && i1 == comps.size() && i0 == 0) return 0; // one chunk: the caller waits for it later
+				CK(cudaStreamSynchronize(strm));
+				lap("dp kernels");
+				if (getenv("PSC_DEBUG_DP")) {
+					std::vector<long long> h((size_t)nUnits * 8);
+					cudaMemcpy(h.data(), st.dp_dbg.p, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+					std::vector<int> ix((size_t)nUnits);
+					for (int u = 0; u < nUnits; ++u) ix[(size_t)u] = u;
+					std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 8] > h[(size_t)b * 8]; });
+					long long tot = 0, totStates = 0, totFrames = 0;
+					for (int u = 0; u < nUnits; ++u) {
+						tot += h[(size_t)u * 8];
+						totStates += h[(size_t)u * 8 + 1] & 0xffffffff;
+						totFrames += (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff;
+					}
+					fprintf(stderr, "[dp] %d units, total %.1f Mcycles, %lld states, %lld frames\n", nUnits, tot / 1e6, totStates, totFrames);
+					for (int k = 0; k < 12 && k < nUnits; ++k) {
+						int u = ix[(size_t)k];
+						int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
+						fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld\n", u, c, s,
+						        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
+						        h[(size_t)u * 8] / 1e6, h[(size_t)u * 8 + 1] & 0xffffffff, h[(size_t)u * 8 + 2] & 0xffffffff, h[(size_t)u * 8 + 3] & 0xfff, (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff, h[(size_t)u * 8 + 3] >> 40,
+						        h[(size_t)u * 8 + 1] >> 32, h[(size_t)u * 8 + 2] >> 32);
+					}
+				}
+				i0 = i1;
 			}
-			// note: the offsets of the units we rolled back (mine, on break) were never committed
-			int nUnits = (int)units.size(), nComp = (int)(i1 - i0);
-			std::vector<int> order((size_t)nUnits);
-			for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
-			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
-			if (!st.scratch.ensure((size_t)std::max(sAcc, mAcc) + 16) || !st.dp_tx.ensure((size_t)tAcc + 16) ||
-			    !st.dp_ntx.ensure(sizeof(int) * (size_t)(nUnits + 1)))
-				return ctx->fail("out of device memory (DP scratch)");
-			CK(cudaMemsetAsync(st.dp_ntx.p, 0, sizeof(int) * (size_t)(nUnits + 1), ctx->stream));
-			if (!upload(ctx, st.list, dpList.data() + i0, (size_t)nComp) || !upload(ctx, st.dp_units, units.data(), units.size()) ||
-			    !upload(ctx, st.order, order.data(), order.size()) || !upload(ctx, st.scr_off, mergeOff.data(), mergeOff.size()))
-				return ctx->fail("out of device memory");
-			lap("dp host prep");
-			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			{
-				const int smemPerWarp = ctx->coop == 32 ? 16 * 1024 : 0; // 4 warps -> 64 KB per CTA, 3 CTAs per SM
-				long long *dbgPtr = nullptr;
-				const bool dbgOn = getenv("PSC_DEBUG_DP") != nullptr;
-				if (dbgOn) {
-					if (!st.dp_dbg.ensure(sizeof(long long) * 8 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
-					CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 8 * (size_t)(nUnits + 1), ctx->stream));
-					dbgPtr = st.dp_dbg.as<long long>();
-				}
-#ifndef PSC_CPU_SHIM
-				CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16 * 1024));
-				ctx->ktime_begin(4);
-				k_dp_units<<<launch_grid(ctx, nUnits), 128, 4 * smemPerWarp, ctx->stream>>>(
-				    ctx->gd, sv, st.dp_units.as<DpUnit>(), st.order.as<int>(), nUnits, (char *)st.scratch.p, (char *)st.dp_tx.p,
-				    st.dp_ntx.as<int>(), counter, ctx->coop, smemPerWarp, dbgPtr);
-				ctx->ktime_end();
-#else
-				KLAUNCH(4, k_dp_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, st.dp_units.as<DpUnit>(), st.order.as<int>(), nUnits,
-				        (char *)st.scratch.p, (char *)st.dp_tx.p, st.dp_ntx.as<int>(), counter, ctx->coop, smemPerWarp, dbgPtr);
-#endif
+		return 0;
+	};
+	// The DP kernel ends with a long tail: a handful of (component, sample) units run for most of its duration
+	// while the rest of the GPU idles.  So the heaviest DP components (by constraint count) get a launch of their
+	// own on the main stream, and everything else -- the DP of the remaining components, its merge, and the
+	// per-unit kernels of every other component -- runs next to it on the second stream.
+	std::vector<int> heavy, rest;
+	{
+		const bool forced = getenv("PSC_FORCE_OVERLAP") != nullptr;
+		bool split = (ctx->coop == 32 || forced) && !getenv("PSC_NO_OVERLAP") && !getenv("PSC_DEBUG_DP") &&
+		             (dpList.size() >= 64 || (forced && dpList.size() >= 2));
+		if (split) {
+			std::vector<std::pair<int, int>> byC; // (-max constraints over the samples, component)
+			for (int c : dpList) {
+				int Cmax = 0;
+				for (int s = 0; s < S; ++s) Cmax = std::max(Cmax, ctx->samples[(size_t)s].h_ncon[(size_t)c]);
+				byC.push_back({-Cmax, c});
 			}
-			++launches;
-			CK(cudaGetLastError());
-			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			KLAUNCH(7, k_dp_merge, launch_grid(ctx, nComp), 128, ctx->gd, sv, st.dp_units.as<DpUnit>(), st.list.as<int>(), nComp,
-			        st.dp_ntx.as<int>(), (const char *)st.dp_tx.p, (char *)st.scratch.p, st.scr_off.as<long long>(), counter, ctx->coop);
-			++launches;
-			CK(cudaGetLastError());
-			CK(cudaStreamSynchronize(ctx->stream));
-			lap("dp kernels");
-			if (getenv("PSC_DEBUG_DP")) {
-				std::vector<long long> h((size_t)nUnits * 8);
-				cudaMemcpy(h.data(), st.dp_dbg.p, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
-				std::vector<int> ix((size_t)nUnits);
-				for (int u = 0; u < nUnits; ++u) ix[(size_t)u] = u;
-				std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 8] > h[(size_t)b * 8]; });
-				long long tot = 0, totStates = 0, totFrames = 0;
-				for (int u = 0; u < nUnits; ++u) {
-					tot += h[(size_t)u * 8];
-					totStates += h[(size_t)u * 8 + 1] & 0xffffffff;
-					totFrames += (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff;
-				}
-				fprintf(stderr, "[dp] %d units, total %.1f Mcycles, %lld states, %lld frames\n", nUnits, tot / 1e6, totStates, totFrames);
-				for (int k = 0; k < 12 && k < nUnits; ++k) {
-					int u = ix[(size_t)k];
-					int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
-					fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld\n", u, c, s,
-					        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
-					        h[(size_t)u * 8] / 1e6, h[(size_t)u * 8 + 1] & 0xffffffff, h[(size_t)u * 8 + 2] & 0xffffffff, h[(size_t)u * 8 + 3] & 0xfff, (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff, h[(size_t)u * 8 + 3] >> 40,
-					        h[(size_t)u * 8 + 1] >> 32, h[(size_t)u * 8 + 2] >> 32);
-				}
-			}
-			i0 = i1;
+			std::sort(byC.begin(), byC.end());
+			size_t nH = std::min<size_t>(std::max<size_t>(dpList.size() / 16, 1), (size_t)ctx->n_sm);
+			if (forced && dpList.size() < 64) nH = std::max<size_t>(dpList.size() / 4, 1);
+			std::vector<char> isH((size_t)nc, 0);
+			for (size_t k = 0; k < nH; ++k) isH[(size_t)byC[k].second] = 1;
+			for (int c : dpList) (isH[(size_t)c] ? heavy : rest).push_back(c);
+			for (int c : heavy) group[(size_t)c] = 2;
 		}
+	}
+	size_t pass1Tx = 0;
+	bool twoPasses = false;
+	if (!heavy.empty()) {
+		if (run_dp(heavy, ctx->stream, st.db[0], counter, false) != 0) return 1;
+		if (run_dp(rest, ctx->stream2, st.db[1], counter + 8, true) != 0) return 1;
+		CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream2));
+		CK(cudaStreamSynchronize(ctx->stream2));
+		if (run_units(1, ctx->stream2, st.ub[1], counter + 8) != 0) return 1;
+		pass1Tx = st.r_comp.size();
+		twoPasses = true;
+		lap("second stream (rest of DP, other components)");
+		CK(cudaStreamSynchronize(ctx->stream));
+		lap("heavy DP tail");
+	} else if (!dpList.empty()) {
+		if (run_dp(dpList, ctx->stream, st.db[1], counter, true) != 0) return 1;
 	}
 	CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-
-	// ---- P3..P6 per chunk of components ----
-	int c0 = 0;
-	while (c0 < nc) {
-		std::vector<long long> scrOff, predOff;
-		std::vector<long long> cost;
-		long long sAcc = 0, pAcc = 0;
-		int c1 = c0;
-		while (c1 < nc) {
-			int n = ctx->h_comp_off[(size_t)c1 + 1] - ctx->h_comp_off[(size_t)c1];
-			int A = st.h_n_cand[(size_t)c1];
-			long long sNeed = 0, pNeed = 0;
-			std::vector<long long> so((size_t)S), po((size_t)S);
-			for (int s = 0; s < S; ++s) {
-				int M = ctx->samples[(size_t)s].h_npair[(size_t)c1], C = ctx->samples[(size_t)s].h_ncon[(size_t)c1];
-				int cap = std::max(1, std::min(A, M + 1));
-				so[(size_t)s] = sNeed;
-				po[(size_t)s] = pNeed;
-				sNeed += (long long)unit_scratch_layout(nullptr, nullptr, A, M, cap, n, C, ctx->h_comp_ng[(size_t)c1], ctx->h_next_cnt[(size_t)c1]);
-				pNeed += (long long)unit_pred_layout(nullptr, nullptr, cap);
-			}
-			if (c1 > c0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
-			for (int s = 0; s < S; ++s) {
-				scrOff.push_back(sAcc + so[(size_t)s]);
-				predOff.push_back(pAcc + po[(size_t)s]);
-				int M = ctx->samples[(size_t)s].h_npair[(size_t)c1];
-				cost.push_back((long long)A * (M + 1));
-			}
-			sAcc += sNeed;
-			pAcc += pNeed;
-			++c1;
-		}
-		scrOff.push_back(sAcc);
-		predOff.push_back(pAcc);
-		int nUnits = (c1 - c0) * S;
-		std::vector<int> order((size_t)nUnits);
-		for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
-		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
-		ok = st.scratch.ensure((size_t)sAcc + 16) && st.pred.ensure((size_t)pAcc + 16) &&
-		     upload(ctx, st.scr_off, scrOff.data(), scrOff.size()) && upload(ctx, st.pred_off, predOff.data(), predOff.size()) &&
-		     upload(ctx, st.order, order.data(), order.size()) && st.n_pred.ensure(sizeof(int) * (size_t)nUnits) &&
-		     st.n_raw.ensure(sizeof(int) * (size_t)nUnits) && st.n_exon.ensure(sizeof(int) * (size_t)nUnits);
-		if (!ok) return ctx->fail("out of device memory (unit scratch)");
-		lap("units host prep");
-		ChunkDev ch;
-		ch.c0 = c0;
-		ch.c1 = c1;
-		ch.scratch_off = st.scr_off.as<long long>();
-		ch.scratch = (char *)st.scratch.p;
-		ch.pred_off = st.pred_off.as<long long>();
-		ch.pred = (char *)st.pred.p;
-		ch.n_pred = st.n_pred.as<int>();
-		ch.n_raw = st.n_raw.as<int>();
-		ch.n_exon = st.n_exon.as<int>();
-		CK(cudaMemsetAsync(ch.n_pred, 0, sizeof(int) * (size_t)nUnits, ctx->stream));
-		CK(cudaMemsetAsync(ch.n_raw, 0, sizeof(int) * (size_t)nUnits, ctx->stream));
-		CK(cudaMemsetAsync(ch.n_exon, 0, sizeof(int) * (size_t)nUnits, ctx->stream));
-		for (int phase = 1; phase <= 3; ++phase) {
-			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			KLAUNCH(phase == 1 ? 5 : (phase == 2 ? 8 : 9), k_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, ch, phase, st.order.as<int>(), counter, ctx->coop);
-			++launches;
-			CK(cudaGetLastError());
-		}
-		std::vector<int> hPred((size_t)nUnits), hExon((size_t)nUnits);
-		CK(cudaMemcpyAsync(hPred.data(), ch.n_pred, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaMemcpyAsync(hExon.data(), ch.n_exon, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaStreamSynchronize(ctx->stream));
-		lap("units kernels");
-		std::vector<long long> txOff((size_t)nUnits + 1), exOff((size_t)nUnits + 1);
-		long long nt = 0, ne = 0;
-		for (int u = 0; u < nUnits; ++u) {
-			txOff[(size_t)u] = nt;
-			exOff[(size_t)u] = ne;
-			nt += hPred[(size_t)u];
-			ne += hExon[(size_t)u];
-		}
-		txOff[(size_t)nUnits] = nt;
-		exOff[(size_t)nUnits] = ne;
-		if (nt > 0) {
-			ok = upload(ctx, st.tx_off, txOff.data(), txOff.size()) && upload(ctx, st.ex_off, exOff.data(), exOff.size()) &&
-			     st.o_comp.ensure(sizeof(int) * (size_t)nt) && st.o_sample.ensure(sizeof(int) * (size_t)nt) &&
-			     st.o_chr.ensure(sizeof(int) * (size_t)nt) && st.o_gene.ensure(sizeof(int) * (size_t)nt) &&
-			     st.o_strand.ensure((size_t)nt) && st.o_exon_off.ensure(sizeof(long long) * (size_t)nt) &&
-			     st.o_exon_start.ensure(sizeof(int) * (size_t)(ne + 1)) && st.o_exon_end.ensure(sizeof(int) * (size_t)(ne + 1)) &&
-			     st.o_fpkm.ensure(sizeof(double) * (size_t)nt) && st.o_cov.ensure(sizeof(double) * (size_t)nt);
-			if (!ok) return ctx->fail("out of device memory (output)");
-			OutDev o;
-			o.comp = st.o_comp.as<int>();
-			o.sample = st.o_sample.as<int>();
-			o.chr = st.o_chr.as<int>();
-			o.gene = st.o_gene.as<int>();
-			o.strand = st.o_strand.as<int8_t>();
-			o.exon_off = st.o_exon_off.as<long long>();
-			o.exon_start = st.o_exon_start.as<int>();
-			o.exon_end = st.o_exon_end.as<int>();
-			o.fpkm = st.o_fpkm.as<double>();
-			o.cov = st.o_cov.as<double>();
-			lap("emit host prep");
-			CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-			KLAUNCH(6, k_emit, launch_grid(ctx, nUnits), 128, ctx->gd, sv, ch, o, st.tx_off.as<long long>(), st.ex_off.as<long long>(),
-			        counter, ctx->coop);
-			++launches;
-			CK(cudaGetLastError());
-			size_t t0 = st.r_comp.size(), e0 = st.r_exon_start.size();
-			st.r_comp.resize(t0 + (size_t)nt); st.r_sample.resize(t0 + (size_t)nt); st.r_chr.resize(t0 + (size_t)nt);
-			st.r_gene.resize(t0 + (size_t)nt); st.r_strand.resize(t0 + (size_t)nt); st.r_fpkm.resize(t0 + (size_t)nt);
-			st.r_cov.resize(t0 + (size_t)nt); st.r_exon_start.resize(e0 + (size_t)ne); st.r_exon_end.resize(e0 + (size_t)ne);
-			std::vector<long long> eo((size_t)nt);
-			CK(cudaMemcpyAsync(st.r_comp.data() + t0, o.comp, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(st.r_sample.data() + t0, o.sample, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(st.r_chr.data() + t0, o.chr, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(st.r_gene.data() + t0, o.gene, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(st.r_strand.data() + t0, o.strand, (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(st.r_fpkm.data() + t0, o.fpkm, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(st.r_cov.data() + t0, o.cov, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(eo.data(), o.exon_off, sizeof(long long) * (size_t)nt, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(st.r_exon_start.data() + e0, o.exon_start, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(st.r_exon_end.data() + e0, o.exon_end, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaStreamSynchronize(ctx->stream));
-			lap("emit + copy back");
-			st.r_exon_off.pop_back();
-			for (long long k = 0; k < nt; ++k) st.r_exon_off.push_back((long long)e0 + eo[(size_t)k]);
-			st.r_exon_off.push_back((long long)e0 + ne);
-		}
-		c0 = c1;
-	}
+	if (run_units(twoPasses ? 2 : 0, ctx->stream, st.ub[0], counter) != 0) return 1;
+	if (twoPasses) merge_passes(st, pass1Tx);
 	lap("exon offsets");
 	int herr = 0;
 	CK(cudaMemcpyAsync(&herr, sv.error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

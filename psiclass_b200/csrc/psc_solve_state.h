@@ -1,10 +1,42 @@
 // psc_solve_state.h -- host-side buffers of psc_solve (included by psc_api.cu after DevBuf)
 #pragma once
+// device buffers of one pass of the per-unit kernels (pick / refine / EM / emit).  Two sets: the pass over
+// the enumerated components runs on its own stream while the DP kernel is still busy on the main one.
+struct UnitBufs {
+	DevBuf scr_off, scratch, pred_off, pred, n_pred, n_raw, n_exon, order, tx_off, ex_off;
+	DevBuf o_comp, o_sample, o_chr, o_gene, o_strand, o_exon_off, o_exon_start, o_exon_end, o_fpkm, o_cov;
+	void release()
+	{
+		DevBuf *all[] = {&scr_off, &scratch, &pred_off, &pred, &n_pred, &n_raw, &n_exon, &order, &tx_off, &ex_off, &o_comp,
+		                 &o_sample, &o_chr, &o_gene, &o_strand, &o_exon_off, &o_exon_start, &o_exon_end, &o_fpkm, &o_cov};
+		for (DevBuf *b : all) b->release();
+	}
+};
+
+// device buffers of one DP launch sequence (k_dp_units + k_dp_merge)
+struct DpBufs {
+	DevBuf list, dp_scr_off, dp_order, dp_tx, dp_ntx, dp_units;
+	DevBuf *scratch = nullptr;
+	void release()
+	{
+		DevBuf *all[] = {&list, &dp_scr_off, &dp_order, &dp_tx, &dp_ntx, &dp_units};
+		for (DevBuf *b : all) b->release();
+	}
+};
+
 struct SolveState {
 	DevBuf can_start, can_end, edge_support, cs00, at_cnt, use_dp, def_gene, n_cand, cand_row_off, cand_bits_off,
-	    cand_bits, cand_first, cand_last, cand_corr, cand_sup1, cand_sup2, error_flag, fscratch, fs_off, list, scr_off,
-	    scratch, pred_off, pred, n_pred, n_raw, n_exon, order, dp_order, tx_off, ex_off, stk, dp_tx, dp_ntx, dp_units, dp_dbg;
-	DevBuf o_comp, o_sample, o_chr, o_gene, o_strand, o_exon_off, o_exon_start, o_exon_end, o_fpkm, o_cov;
+	    cand_bits, cand_first, cand_last, cand_corr, cand_sup1, cand_sup2, error_flag, fscratch, fs_off, list, stk, dp_dbg,
+	    dp_heavy_scratch;
+	UnitBufs ub[2];
+	// db[0]: the heavy DP components (own scratch); db[1]: the others, in ub[0].scratch (that DP is over before
+	// the pass that uses ub[0] starts)
+	DpBufs db[2];
+	SolveState()
+	{
+		db[0].scratch = &dp_heavy_scratch;
+		db[1].scratch = &ub[0].scratch;
+	}
 	std::vector<int> h_at_cnt, h_use_dp, h_n_cand;
 	// results, host side (filled chunk by chunk)
 	std::vector<int> r_comp, r_sample, r_chr, r_gene, r_exon_start, r_exon_end;
@@ -15,10 +47,11 @@ struct SolveState {
 	{
 		DevBuf *all[] = {&can_start, &can_end, &edge_support, &cs00, &at_cnt, &use_dp, &def_gene, &n_cand,
 		                 &cand_row_off, &cand_bits_off, &cand_bits, &cand_first, &cand_last, &cand_corr, &cand_sup1,
-		                 &cand_sup2, &error_flag, &fscratch, &fs_off, &list, &scr_off, &scratch, &pred_off, &pred,
-		                 &n_pred, &n_raw, &n_exon, &order, &dp_order, &tx_off, &ex_off, &stk, &dp_tx, &dp_ntx, &dp_units, &dp_dbg, &o_comp, &o_sample,
-		                 &o_chr, &o_gene, &o_strand, &o_exon_off, &o_exon_start, &o_exon_end, &o_fpkm, &o_cov};
+		                 &cand_sup2, &error_flag, &fscratch, &fs_off, &list, &stk, &dp_dbg, &dp_heavy_scratch};
 		for (DevBuf *b : all) b->release();
+		ub[0].release();
+		ub[1].release();
+		db[0].release();
+		db[1].release();
 	}
 };
-

@@ -44,6 +44,16 @@ def test_one_thread_per_unit_agrees_with_warp_per_unit(cfg):
     assert rep.passed, rep.summary()
 
 
+@pytest.mark.parametrize("cfg", CONFIGS[2:4])
+def test_two_stream_schedule_matches_oracle(cfg, monkeypatch):
+    """Large workloads run the heaviest DP components on the main stream and everything else on a second
+    one, then merge the two result lists back into component order; force that schedule on a small set."""
+    monkeypatch.setenv("PSC_FORCE_OVERLAP", "1")
+    wl = testkit.Workload.synth(threads=8, **cfg)
+    rep = wl.check(abi.LIB_PATH, coop=32)
+    assert rep.passed, rep.summary()
+
+
 def test_flags_unlimited_dp_and_primary_paralog():
     wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=8)
     assert wl.check(abi.LIB_PATH, max_dp=-1).passed

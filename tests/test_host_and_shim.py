@@ -26,6 +26,15 @@ def test_kernel_logic_matches_oracle_on_cpu_shim(cfg):
     assert rep.tables_checked == wl.n_comp * wl.n_samples and rep.val_close == 0
 
 
+def test_two_pass_schedule_keeps_component_major_output(monkeypatch):
+    """On a GPU the enumerated components' per-unit kernels run on a second stream under the DP kernel and
+    the two result lists are merged back into component order; force that schedule in the serial shim."""
+    monkeypatch.setenv("PSC_FORCE_OVERLAP", "1")
+    wl = testkit.Workload.synth(seed=42, n_genes=30, n_samples=4, mean_pairs=200.0, exon_mu=2.2, iso_lambda=4.0, p_alt=0.3, p_ir=0.1, threads=4)
+    rep = wl.check(testkit.SHIM_PATH, coop=1)
+    assert rep.passed, rep.summary()
+
+
 def test_unlimited_dp_constraints_and_paralog_flag():
     wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=4)
     assert wl.check(testkit.SHIM_PATH, coop=1, max_dp=-1).passed
