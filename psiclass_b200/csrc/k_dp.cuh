@@ -60,7 +60,8 @@ struct DpScratch {
 	int *c2f, *c2l;
 };
 
-#define PSC_FR_INTS 10
+// frame memory of the walk: 5 ints per path position, 10 per owner (k_dp_walk.cuh)
+#define PSC_FR_INTS_TOTAL(n) (15 * (n) + 64)
 __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, int n, int E, int Cmax, long long candCap)
 {
 	Carver cv(base);
@@ -85,7 +86,7 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 	s.tcCnt = 0;
 	s.uncov = cv.take<uint8_t>((size_t)E + 1);
 	s.P = cv.take<int>((size_t)n + 4);
-	s.fr = cv.take<int>((size_t)(2 * n + 6) * PSC_FR_INTS);
+	s.fr = cv.take<int>((size_t)PSC_FR_INTS_TOTAL(n));
 	s.fdcover = cv.take<double>((size_t)n + 3);
 	s.fdbeta = cv.take<double>((size_t)n + 3);
 	s.fdmeta = cv.take<int>((size_t)(n + 3) * 4);
@@ -876,7 +877,7 @@ PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
 	if (!sm) return;
 	Carver cv(sm);
 	int *P = cv.take<int>((size_t)n + 4);
-	int *fr = cv.take<int>((size_t)(2 * n + 6) * PSC_FR_INTS);
+	int *fr = cv.take<int>((size_t)PSC_FR_INTS_TOTAL(n));
 	double *fdcover = cv.take<double>((size_t)n + 3);
 	double *fdbeta = cv.take<double>((size_t)n + 3);
 	int *fdmeta = cv.take<int>((size_t)(n + 3) * 4);

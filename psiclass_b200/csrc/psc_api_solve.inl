@@ -36,6 +36,13 @@ __global__ void __launch_bounds__(128) k_enumerate(GraphDev g, SolveDev sv, cons
 	}
 }
 
+// Optional shared-memory slice per warp for the walk's frame memory.  Measured on B200 (full bench workload,
+// total DP cycles / heaviest unit): 0 KB 1.78e12 / 2.73e9, 8 KB 1.83e12 / 3.27e9, 16 KB 1.81e12 / 3.08e9,
+// 26 KB 2.07e12 / 3.31e9 -- since the walk keeps its hot state in registers, the L1 capacity the carve-out
+// takes away costs more than the shorter latency gives.  So: off.
+#ifndef PSC_DP_SMEM_PER_WARP
+#define PSC_DP_SMEM_PER_WARP 0
+#endif
 #ifndef PSC_DP_MINBLOCKS
 #define PSC_DP_MINBLOCKS 1
 #endif
@@ -522,7 +529,7 @@ int psc_solve(psc_ctx *ctx)
 				lap("dp host prep");
 				CK(cudaMemsetAsync(cnt, 0, 32, strm));
 				{
-					const int smemPerWarp = ctx->coop == 32 ? 16 * 1024 : 0; // 4 warps -> 64 KB per CTA, 3 CTAs per SM
+					const int smemPerWarp = ctx->coop == 32 ? PSC_DP_SMEM_PER_WARP : 0; // x 4 warps per CTA, 2 CTAs per SM (255 registers)
 					long long *dbgPtr = nullptr;
 					const bool dbgOn = getenv("PSC_DEBUG_DP") != nullptr;
 					if (dbgOn) {
@@ -531,7 +538,7 @@ int psc_solve(psc_ctx *ctx)
 						dbgPtr = st.dp_dbg.as<long long>();
 					}
 	#ifndef PSC_CPU_SHIM
-					CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16 * 1024));
+					CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PSC_DP_SMEM_PER_WARP));
 					ctx->ktime_begin(4, strm);
 					k_dp_units<<<launch_grid(ctx, nUnits), 128, 4 * smemPerWarp, strm>>>(
 					    ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits, (char *)(*db.scratch).p, (char *)db.dp_tx.p,
