@@ -76,6 +76,9 @@ __host__ __device__ inline size_t unit_pred_layout(UnitPred *o, char *base, int 
 }
 
 // per-unit scratch of PickTranscripts / AbundanceEstimation / RefineTranscripts
+#ifndef PSC_OL
+#define PSC_OL 12
+#endif
 struct UnitScratch {
 	uint64_t *btable;  // [A * MW]
 	double *tAbund, *avgAbund, *covPortion, *coverCnt, *abund; // [A]
@@ -87,6 +90,8 @@ struct UnitScratch {
 	double *score;     // [A] cached ComputeScore of the candidate, -1: not selectable
 	double *contrib;   // [M] this iteration's support of maxtag per pair, -1: pair was already depleted
 	int *picked;       // [cap] candidates owning a csupport row, ascending
+	int *ocnt;         // [M] number of candidates that ever held support for the pair, -1: more than PSC_OL
+	int *olist;        // [M * PSC_OL] those candidates, ascending
 	int *reach;        // [32 * n] per-lane scratch of the chain-coverage pass
 	double *persist;   // [4] inf, any-compatible flag, maxAbundance: round 1 -> round 2
 	uint64_t *tmpbits; // [4 * W]
@@ -121,6 +126,8 @@ __host__ __device__ inline size_t unit_scratch_layout(UnitScratch *o, char *base
 	s.score = cv.take<double>((size_t)A);
 	s.contrib = cv.take<double>((size_t)M + 1);
 	s.picked = cv.take<int>((size_t)cap + 1);
+	s.ocnt = cv.take<int>((size_t)M + 1);
+	s.olist = cv.take<int>((size_t)M * PSC_OL + 1);
 	s.reach = cv.take<int>((size_t)32 * n);
 	s.persist = cv.take<double>(4);
 	s.tmpbits = cv.take<uint64_t>((size_t)4 * W);
@@ -492,12 +499,16 @@ PSC_DEV bool pair_in_tx(const TableView &t, int j, const uint64_t *tb, int tf, i
 	       compat(tb, tf, tl, false, t.bits + (long long)b * W, t.first[b], t.last[b], W) == 1;
 }
 
-// One row of the compatibility bit-matrix (btable[i], .cpp:1426-1442): the 32 lanes test 32 mate
-// pairs at a time and a warp ballot packs the results into one 32-bit half word.
-// Returns non-zero (in every lane) if any bit of the row is set.
+// One row of the compatibility bit-matrix (btable[i], .cpp:1426-1442).  A mate pair is compatible when both
+// of its constraints are, and a component has far fewer constraints than pairs: so the lanes first test
+// the C constraints once (flags[]), then a pair costs two byte lookups; a warp ballot packs 32 pairs into
+// one 32-bit half word.  Returns non-zero (in every lane) if any bit of the row is set.
 PSC_DEV int build_pair_row(const Coop &co, const TableView &t, const uint64_t *tb, int tf, int tl, int W, int M, int MW,
-                           uint64_t *row)
+                           uint64_t *row, uint8_t *flags)
 {
+	for (int c = co.lane; c < t.C; c += co.n)
+		flags[c] = compat(tb, tf, tl, false, t.bits + (long long)c * W, t.first[c], t.last[c], W) == 1;
+	co.sync();
 	uint32_t *row32 = (uint32_t *)row;
 	int any = 0;
 	int n32 = 2 * MW;
@@ -506,17 +517,18 @@ PSC_DEV int build_pair_row(const Coop &co, const TableView &t, const uint64_t *t
 		int j0 = k * 32;
 		if (co.n > 1) {
 			int j = j0 + co.lane;
-			bool in = j < M && pair_in_tx(t, j, tb, tf, tl, W);
+			bool in = j < M && flags[t.pi[j]] && flags[t.pj[j]];
 			mask = co.ballot(in);
 		} else {
 			for (int b = 0; b < 32; ++b) {
 				int j = j0 + b;
-				if (j < M && pair_in_tx(t, j, tb, tf, tl, W)) mask |= 1u << b;
+				if (j < M && flags[t.pi[j]] && flags[t.pj[j]]) mask |= 1u << b;
 			}
 		}
 		if (co.lane == 0) row32[k] = mask;
 		if (mask) any = 1;
 	}
+	co.sync(); // flags[] is rewritten for the next row
 	return any;
 }
 
@@ -527,6 +539,28 @@ PSC_DEV int build_pair_row(const Coop &co, const TableView &t, const uint64_t *t
 // reuses what the first one left in the unit's scratch.
 // output: pr.id / pr.abundance / pr.corr, returns the number picked
 // =============================================================================================
+// remember that candidate `cand` holds support for pair j (its csupport entry left zero): the redistribution
+// step only has to look at these candidates.  Lists longer than PSC_OL fall back to the scan of all row owners.
+PSC_DEV void pair_owner_add(const UnitScratch &sc, int j, int cand)
+{
+	int c = sc.ocnt[j];
+	if (c < 0) return;
+	int *L = sc.olist + (long long)j * PSC_OL;
+	for (int q = 0; q < c; ++q)
+		if (L[q] == cand) return;
+	if (c == PSC_OL) {
+		sc.ocnt[j] = -1;
+		return;
+	}
+	int q = c;
+	while (q > 0 && L[q - 1] > cand) {
+		L[q] = L[q - 1];
+		--q;
+	}
+	L[q] = cand;
+	sc.ocnt[j] = c + 1;
+}
+
 PSC_DEV double pick_score(const UnitScratch &sc, const CandView &cd, const SolveParams &prm, int i, double cnt,
                           double maxAbundance, bool round2)
 {
@@ -559,7 +593,7 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		int anySet = 0;
 		for (int i = 0; i < A; ++i)
 			anySet |= build_pair_row(co, t, cd.bits + (long long)i * W, cd.first[i], cd.last[i], W, M, MW,
-			                         sc.btable + (long long)i * MW);
+			                         sc.btable + (long long)i * MW, sc.flagsA);
 		anySet = co.max(anySet);
 		co.sync();
 		if (co.lane == 0) {
@@ -669,7 +703,10 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 		maxAbundance = sc.persist[2];
 	}
 	// ---- per-round state ----
-	for (int j = co.lane; j < M; j += co.n) sc.pairAbund[j] = t.pnorm[j];
+	for (int j = co.lane; j < M; j += co.n) {
+		sc.pairAbund[j] = t.pnorm[j];
+		sc.ocnt[j] = 0;
+	}
 	co.sync();
 	for (int i = co.lane; i < A; i += co.n) {
 		sc.abund[i] = 0;
@@ -774,6 +811,7 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 					pa -= 1 * update;
 					double factor = t.pec[j];
 					double tmp = (t.psup[j] * update / t.pnorm[j] * factor);
+					if (rowm[j] == 0 && tmp != 0) pair_owner_add(sc, j, maxtag);
 					rowm[j] += tmp;
 					sc.contrib[j] = tmp;
 					if (pa <= 0) sc.depl[atomic_add(dcount, 1)] = j;
@@ -807,11 +845,15 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 						// Only candidates that were picked before can have abundance > 0: walk the (index-sorted)
 						// list of row owners instead of all A candidates.
 						double takeOut = 0, factor = t.pec[j];
-						for (int p0 = 0; p0 < poolUsed; p0 += co.n) {
+						// the candidates that ever held support for pair j (ascending), or all row owners
+						const int oc = sc.ocnt[j];
+						const int *ol = oc >= 0 ? sc.olist + (long long)j * PSC_OL : sc.picked;
+						const int on = oc >= 0 ? oc : poolUsed;
+						for (int p0 = 0; p0 < on; p0 += co.n) {
 							int pq = p0 + co.lane;
 							double tmp = 0;
-							if (pq < poolUsed) {
-								int i = sc.picked[pq];
+							if (pq < on) {
+								int i = ol[pq];
 								if (i != maxtag && sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j))
 									tmp = sc.pool[(long long)sc.slot[i] * M + j] * tam / (tam + sc.tAbund[i]);
 							}
@@ -830,9 +872,9 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 							if (takeOut > (t.psup[j] * factor) * takeOutFactor)
 								ratio = (t.psup[j] * factor) * takeOutFactor / takeOut;
 						}
-						if (takeOut > 0)
-							for (int pq = co.lane; pq < poolUsed; pq += co.n) {
-								int i = sc.picked[pq];
+						if (takeOut > 0) {
+							for (int pq = co.lane; pq < on; pq += co.n) {
+								int i = ol[pq];
 								if (i != maxtag && sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
 									double *ri = sc.pool + (long long)sc.slot[i] * M;
 									double tmp = ri[j] * tam / (tam + sc.tAbund[i]);
@@ -843,8 +885,13 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 									}
 								}
 							}
+							co.sync(); // the next pair may hand the same candidate to another lane
+						}
 						double tmp = takeOut * ratio;
-						if (co.lane == 0) rowm[j] += tmp;
+						if (co.lane == 0) {
+							if (tmp != 0) pair_owner_add(sc, j, maxtag);
+							rowm[j] += tmp;
+						}
 						abm += tmp;
 					}
 				}

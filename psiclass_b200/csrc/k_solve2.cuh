@@ -42,7 +42,7 @@ PSC_DEV void abundance_em(const Coop &co, const CompView &v, const TableView &t,
 	if (T <= 0) return;
 	int MW = (M + 63) >> 6;
 	for (int i = 0; i < T; ++i)
-		build_pair_row(co, t, pv.bits(i), pv.first(i), pv.last(i), W, M, MW, sc.ebtable + (long long)i * MW);
+		build_pair_row(co, t, pv.bits(i), pv.first(i), pv.last(i), W, M, MW, sc.ebtable + (long long)i * MW, sc.flagsA);
 	co.sync();
 	for (int i = co.lane; i < T; i += co.n) {
 		int len = tx_len(v, pv.bits(i), pv.first(i), pv.last(i));
