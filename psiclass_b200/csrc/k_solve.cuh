@@ -864,15 +864,16 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 								takeOut += co.bcast(tmp, bsrc);
 							}
 						}
-						double ratio = 1, takeOutFactor = 0.5;
-						if (update < t.pnorm[j]) {
-							if (takeOut > (t.psup[j] * update / t.pnorm[j] * factor) * takeOutFactor)
-								ratio = (t.psup[j] * update / t.pnorm[j] * factor) * takeOutFactor / takeOut;
-						} else {
-							if (takeOut > (t.psup[j] * factor) * takeOutFactor)
-								ratio = (t.psup[j] * factor) * takeOutFactor / takeOut;
-						}
+						// nothing to take from: the share stays 0 and the sums below would add 0.0
 						if (takeOut > 0) {
+							double ratio = 1, takeOutFactor = 0.5;
+							if (update < t.pnorm[j]) {
+								if (takeOut > (t.psup[j] * update / t.pnorm[j] * factor) * takeOutFactor)
+									ratio = (t.psup[j] * update / t.pnorm[j] * factor) * takeOutFactor / takeOut;
+							} else {
+								if (takeOut > (t.psup[j] * factor) * takeOutFactor)
+									ratio = (t.psup[j] * factor) * takeOutFactor / takeOut;
+							}
 							for (int pq = co.lane; pq < on; pq += co.n) {
 								int i = ol[pq];
 								if (i != maxtag && sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
@@ -886,13 +887,13 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 								}
 							}
 							co.sync(); // the next pair may hand the same candidate to another lane
+							double tmp = takeOut * ratio;
+							if (co.lane == 0) {
+								if (tmp != 0) pair_owner_add(sc, j, maxtag);
+								rowm[j] += tmp;
+							}
+							abm += tmp;
 						}
-						double tmp = takeOut * ratio;
-						if (co.lane == 0) {
-							if (tmp != 0) pair_owner_add(sc, j, maxtag);
-							rowm[j] += tmp;
-						}
-						abm += tmp;
 					}
 				}
 			}

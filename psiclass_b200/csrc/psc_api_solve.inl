@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const
 // phase: 1 pick round 1, 2 pick round 2 + filtration, 3 rescue.  list[0 .. nList): the chunk-local units of this pass,
 // heaviest first
 __global__ void __launch_bounds__(128, 4) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *list, int nList,
-                                               int *counter, int width)
+                                               int *counter, int width, long long *dbg)
 {
 	Coop co = make_coop(width);
 	int S = sv.prm.S;
@@ -100,10 +100,12 @@ __global__ void __launch_bounds__(128, 4) k_units(GraphDev g, SolveDev sv, Chunk
 		if (u >= nList) break;
 		int ul = list[u];
 		int c = ch.c0 + ul / S, s = ul % S;
+		long long t0 = dbg ? clock64() : 0;
 		if (phase == 1) unit_pick_round1(co, g, sv, ch, c, s);
 		else if (phase == 2) unit_pick_round2(co, g, sv, ch, c, s);
 		else unit_rescue(co, g, sv, ch, c, s);
 		co.sync();
+		if (dbg && co.lane == 0) dbg[(long long)ul * 3 + (phase - 1)] = clock64() - t0; // PSC_DEBUG_UNITS
 	}
 }
 
@@ -376,14 +378,38 @@ int psc_solve(psc_ctx *ctx)
 			CK(cudaMemsetAsync(ch.n_pred, 0, sizeof(int) * (size_t)nUnits, strm));
 			CK(cudaMemsetAsync(ch.n_raw, 0, sizeof(int) * (size_t)nUnits, strm));
 			CK(cudaMemsetAsync(ch.n_exon, 0, sizeof(int) * (size_t)nUnits, strm));
+			long long *unitDbg = nullptr;
+			if (getenv("PSC_DEBUG_UNITS")) {
+				if (!st.dp_dbg.ensure(sizeof(long long) * 3 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
+				CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 3 * (size_t)(nUnits + 1), strm));
+				unitDbg = st.dp_dbg.as<long long>();
+			}
 			for (int phase = 1; phase <= 3; ++phase) {
 				CK(cudaMemsetAsync(cnt, 0, 32, strm));
-				KLAUNCH_ON(strm, phase == 1 ? 5 : (phase == 2 ? 8 : 9), k_units, launch_grid(ctx, nList), 128, ctx->gd, sv, ch, phase, ub.order.as<int>(), nList, cnt, ctx->coop);
+				KLAUNCH_ON(strm, phase == 1 ? 5 : (phase == 2 ? 8 : 9), k_units, launch_grid(ctx, nList), 128, ctx->gd, sv, ch, phase, ub.order.as<int>(), nList, cnt, ctx->coop, unitDbg);
 				++launches;
 				CK(cudaGetLastError());
 				if (hostDbg) {
 					CK(cudaStreamSynchronize(strm));
 					lap(phase == 1 ? "  units phase 1 (pick)" : (phase == 2 ? "  units phase 2 (pick, refine, EM)" : "  units phase 3 (rescue)"));
+				}
+			}
+			if (unitDbg) { // PSC_DEBUG_UNITS=1: the slowest (component, sample) units of this pass
+				CK(cudaStreamSynchronize(strm));
+				std::vector<long long> h((size_t)nUnits * 3);
+				cudaMemcpy(h.data(), unitDbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+				for (int ph = 0; ph < 2; ++ph) {
+					std::vector<int> ix(order);
+					std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 3 + ph] > h[(size_t)b * 3 + ph]; });
+					long long tot = 0;
+					for (int u : order) tot += h[(size_t)u * 3 + ph];
+					fprintf(stderr, "[units] pass %d phase %d: %d units, total %.1f Mcycles\n", pass, ph + 1, nList, tot / 1e6);
+					for (int k = 0; k < 5 && k < nList; ++k) {
+						int u = ix[(size_t)k], c = c0 + u / S, sm = u % S;
+						fprintf(stderr, "[units]   comp %d sample %d n=%d A=%d C=%d M=%d: %.1f Mcycles\n", c, sm,
+						        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], st.h_n_cand[(size_t)c],
+						        ctx->samples[(size_t)sm].h_ncon[(size_t)c], ctx->samples[(size_t)sm].h_npair[(size_t)c], h[(size_t)u * 3 + ph] / 1e6);
+					}
 				}
 			}
 			std::vector<int> hPred((size_t)nUnits), hExon((size_t)nUnits);
