@@ -321,6 +321,9 @@ def main():
         launches_per_step = max(1, kcnt[dom] // max(1, a.steps))
         alg = kbytes[dom] / launches_per_step
         achieved = (alg / 1e9) / (per_launch_ms / 1e3) if per_launch_ms > 0 and alg > 0 else 0.0
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one `ncu --set full` capture of the
+        # default workload (profiles/r1_ncu_summary.md): the launch over the heavy DP components, 40.0 + 185.2 MB
+        traffic = 225.2e6 if (names[dom] == "dp_units" and not a.genes) else None
         line = {
             "metric": METRIC, "value": total_components * a.steps / wall_max, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * wall_max / a.steps,
@@ -330,7 +333,7 @@ def main():
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_" + names[dom], "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "ms_per_launch": per_launch_ms},
             "kernel_ms_per_step": {names[k]: kms[k] / a.steps for k in range(12) if kcnt[k]},
