@@ -222,6 +222,8 @@ int psc_create(psc_ctx **out, int device)
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
 	size_t fr = 0, tot = 0;
 	if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ctx->mem_budget = fr / 4;
+	// scratch budget per buffer class; work that needs more is cut into chunks of components (tests force tiny budgets)
+	if (const char *e = getenv("PSC_MEM_BUDGET_MB")) ctx->mem_budget = (size_t)atoll(e) << 20;
 	if (cudaStreamCreate(&ctx->stream) != cudaSuccess || cudaStreamCreate(&ctx->stream2) != cudaSuccess ||
 	    cudaEventCreate(&ctx->ev0) != cudaSuccess ||
 	    cudaEventCreate(&ctx->ev1) != cudaSuccess) {

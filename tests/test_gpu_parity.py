@@ -54,6 +54,17 @@ def test_two_stream_schedule_matches_oracle(cfg, monkeypatch):
     assert rep.passed, rep.summary()
 
 
+@pytest.mark.parametrize("force_overlap", [False, True])
+def test_chunked_scratch_budget_matches_oracle(monkeypatch, force_overlap):
+    """A 2 MB scratch budget cuts the DP launches and the per-unit passes into many chunks of components."""
+    monkeypatch.setenv("PSC_MEM_BUDGET_MB", "2")
+    if force_overlap:
+        monkeypatch.setenv("PSC_FORCE_OVERLAP", "1")
+    wl = testkit.Workload.synth(threads=8, **CONFIGS[3])
+    rep = wl.check(abi.LIB_PATH, coop=32)
+    assert rep.passed, rep.summary()
+
+
 def test_flags_unlimited_dp_and_primary_paralog():
     wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=8)
     assert wl.check(abi.LIB_PATH, max_dp=-1).passed

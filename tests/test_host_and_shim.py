@@ -35,6 +35,17 @@ def test_two_pass_schedule_keeps_component_major_output(monkeypatch):
     assert rep.passed, rep.summary()
 
 
+@pytest.mark.parametrize("force_overlap", [False, True])
+def test_chunked_scratch_budget_gives_the_same_answer(monkeypatch, force_overlap):
+    """A 1 MB scratch budget cuts the DP launches and the per-unit passes into many chunks of components."""
+    monkeypatch.setenv("PSC_MEM_BUDGET_MB", "1")
+    if force_overlap:
+        monkeypatch.setenv("PSC_FORCE_OVERLAP", "1")
+    wl = testkit.Workload.synth(seed=42, n_genes=30, n_samples=4, mean_pairs=200.0, exon_mu=2.2, iso_lambda=4.0, p_alt=0.3, p_ir=0.1, threads=4)
+    rep = wl.check(testkit.SHIM_PATH, coop=1)
+    assert rep.passed, rep.summary()
+
+
 def test_unlimited_dp_constraints_and_paralog_flag():
     wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=4)
     assert wl.check(testkit.SHIM_PATH, coop=1, max_dp=-1).passed
