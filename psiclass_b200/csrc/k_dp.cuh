@@ -310,11 +310,16 @@ template <int NW> PSC_DEV int compat_r(const BitsR<NW> &t, int tf, int tl, bool 
 }
 
 // dp_scan_cover with the path bits in registers; the per-constraint decisions are selects, not
-// branches.  Ranges of more than one constraint per lane take two per lane and pass so that their loads
-// and tests overlap.  The warp reductions are kept to one vote, one packed add and -- only when some
-// lane can lower the running minimum -- one minimum.
+// branches.  The warp reductions are kept to one vote, one packed add and -- only when some lane can
+// lower the running minimum -- one minimum.  Deliberately NOT unrolled: the walk is bound by
+// instruction fetch as much as by latency, and every variant with more code per scan (two constraints
+// per lane, a special case for short ranges) measured slower on B200 (total DP cycles of the bench
+// workload: 1.79e12 with both, 1.57e12 without the special case, 1.24e12 with the plain loop).
+#ifndef PSC_SCANR_INLINE
+#define PSC_SCANR_INLINE PSC_DEV
+#endif
 template <int NW>
-PSC_DEV double dp_scan_cover_r(const DpState &st, const BitsR<NW> &t, int tf, int tl, int tcStart, int bound, double cover,
+PSC_SCANR_INLINE double dp_scan_cover_r(const DpState &st, const BitsR<NW> &t, int tf, int tl, int tcStart, int bound, double cover,
                                bool &belowMin, double &beta)
 {
 	int end = dp_tc_end(st, tcStart, bound);
@@ -325,43 +330,20 @@ PSC_DEV double dp_scan_cover_r(const DpState &st, const BitsR<NW> &t, int tf, in
 	bool below = false;
 	int cnt = 0, ccnt = 0;
 	double mn = 1e300, mnAll = 1e300;
-	if (end - tcStart <= L) {
-		int i0 = tcStart + st.co.lane;
-		if (i0 < end) {
-			BitsR<NW> x;
-			x.load(d.tcb + (long long)i0 * W, W);
-			double n0 = d.tcnorm[i0], x0 = d.tcab[i0];
-			bool c0 = compat_r<NW>(t, tf, tl, false, x, d.tcf[i0], d.tcl[i0]) == 1;
-			bool lo0 = n0 <= minAb;
-			below = c0 && lo0;
-			bool in0 = c0 && !lo0, p0 = in0 && x0 > 0;
-			ccnt = in0 ? 1 : 0;
-			cnt = p0 ? 1 : 0;
-			if (in0) mnAll = n0;
-			if (p0) mn = n0;
-		}
-	} else {
-		for (int i0 = tcStart + st.co.lane; i0 < end; i0 += 2 * L) {
-			int i1 = i0 + L;
-			bool v1 = i1 < end;
-			if (!v1) i1 = i0;
-			int f0 = d.tcf[i0], l0 = d.tcl[i0], f1 = d.tcf[i1], l1 = d.tcl[i1];
-			BitsR<NW> y0, y1;
+	{
+		for (int i0 = tcStart + st.co.lane; i0 < end; i0 += L) {
+			BitsR<NW> y0;
 			y0.load(d.tcb + (long long)i0 * W, W);
-			y1.load(d.tcb + (long long)i1 * W, W);
-			double n0 = d.tcnorm[i0], n1 = d.tcnorm[i1], x0 = d.tcab[i0], x1 = d.tcab[i1];
-			bool c0 = compat_r<NW>(t, tf, tl, false, y0, f0, l0) == 1;
-			bool c1 = v1 && compat_r<NW>(t, tf, tl, false, y1, f1, l1) == 1;
-			bool lo0 = n0 <= minAb, lo1 = n1 <= minAb;
-			below = below || (c0 && lo0) || (c1 && lo1);
-			bool in0 = c0 && !lo0, in1 = c1 && !lo1;
-			ccnt += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+			double n0 = d.tcnorm[i0], x0 = d.tcab[i0];
+			bool c0 = compat_r<NW>(t, tf, tl, false, y0, d.tcf[i0], d.tcl[i0]) == 1;
+			bool lo0 = n0 <= minAb;
+			below = below || (c0 && lo0);
+			bool in0 = c0 && !lo0;
+			ccnt += in0 ? 1 : 0;
 			if (in0 && n0 < mnAll) mnAll = n0;
-			if (in1 && n1 < mnAll) mnAll = n1;
-			bool p0 = in0 && x0 > 0, p1 = in1 && x1 > 0;
-			cnt += (p0 ? 1 : 0) + (p1 ? 1 : 0);
+			bool p0 = in0 && x0 > 0;
+			cnt += p0 ? 1 : 0;
 			if (p0 && n0 < mn) mn = n0;
-			if (p1 && n1 < mn) mn = n1;
 		}
 	}
 	// the reference breaks at the FIRST compatible constraint with normAbund <= minAbundance, whatever

@@ -166,27 +166,19 @@ template <int NW> PSC_DEVN long long dp_solve_root_t(DpState &stRef, int start)
 			{
 				int end = dp_tc_end(st, o_tcStart, o_last);
 				if (SMALL) {
-					for (int b0 = o_tcStart; b0 < end; b0 += 2 * co.n) {
-						int i0 = b0 + co.lane, i1 = i0 + co.n;
-						bool v0 = i0 < end, v1 = i1 < end;
-						int j0 = v0 ? i0 : end - 1, j1 = v1 ? i1 : end - 1;
-						BV x0, x1;
+					for (int b0 = o_tcStart; b0 < end; b0 += co.n) {
+						int i0 = b0 + co.lane;
+						bool v0 = i0 < end;
+						int j0 = v0 ? i0 : end - 1;
+						BV x0;
 						x0.load(d.tcb + (long long)j0 * W, W);
-						x1.load(d.tcb + (long long)j1 * W, W);
 						bool is0 = v0 && compat_r<NW>(o_k, o_first, o_last, true, x0, d.tcf[j0], d.tcl[j0]) == 2;
-						bool is1 = v1 && compat_r<NW>(o_k, o_first, o_last, true, x1, d.tcf[j1], d.tcl[j1]) == 2;
 						uint32_t m0 = co.ballot(is0);
 						if (is0) {
 							int p = o_extBase + o_extCnt + co.rank_in(m0);
 							if (p < d.extCap) d.ext[p] = i0;
 						}
 						o_extCnt += popc32(m0);
-						uint32_t m1 = co.ballot(is1);
-						if (is1) {
-							int p = o_extBase + o_extCnt + co.rank_in(m1);
-							if (p < d.extCap) d.ext[p] = i1;
-						}
-						o_extCnt += popc32(m1);
 					}
 				} else {
 					for (int b0 = o_tcStart; b0 < end; b0 += co.n) {
