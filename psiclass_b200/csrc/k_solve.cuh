@@ -849,7 +849,25 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 						const int oc = sc.ocnt[j];
 						const int *ol = oc >= 0 ? sc.olist + (long long)j * PSC_OL : sc.picked;
 						const int on = oc >= 0 ? oc : poolUsed;
-						for (int p0 = 0; p0 < on; p0 += co.n) {
+						// first round: lane q looks at list entry q and keeps what it found for the update below
+						double tmp1 = 0;
+						int i1 = -1;
+						if (co.lane < on) {
+							int i = ol[co.lane];
+							if (i != maxtag && sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
+								i1 = i;
+								tmp1 = sc.pool[(long long)sc.slot[i] * M + j] * tam / (tam + sc.tAbund[i]);
+							}
+						}
+						{
+							uint32_t m = co.ballot(tmp1 > 0);
+							while (m) {
+								int bsrc = ctz32(m);
+								m &= m - 1;
+								takeOut += co.bcast(tmp1, bsrc);
+							}
+						}
+						for (int p0 = co.n; p0 < on; p0 += co.n) { // only the fallback list can be this long
 							int pq = p0 + co.lane;
 							double tmp = 0;
 							if (pq < on) {
@@ -874,7 +892,12 @@ PSC_DEV int pick_transcripts(const Coop &co, const CompView &v, const CandView &
 								if (takeOut > (t.psup[j] * factor) * takeOutFactor)
 									ratio = (t.psup[j] * factor) * takeOutFactor / takeOut;
 							}
-							for (int pq = co.lane; pq < on; pq += co.n) {
+							if (tmp1 > 0) { // same value the first round computed: nothing it depends on has changed
+								double tmp = tmp1 * ratio;
+								sc.pool[(long long)sc.slot[i1] * M + j] -= tmp;
+								sc.abund[i1] -= tmp;
+							}
+							for (int pq = co.n + co.lane; pq < on; pq += co.n) {
 								int i = ol[pq];
 								if (i != maxtag && sc.abund[i] > 0 && bt_test(sc.btable + (long long)i * MW, j)) {
 									double *ri = sc.pool + (long long)sc.slot[i] * M;
