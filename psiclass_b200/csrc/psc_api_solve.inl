@@ -139,33 +139,53 @@ static void merge_passes(SolveState &st, size_t nA)
 		while (a < nA) perm[k++] = a++;
 		while (b < nt) perm[k++] = b++;
 	}
-	auto gather = [&](auto &vec) {
-		typename std::remove_reference<decltype(vec)>::type out(vec.size());
-		for (size_t k = 0; k < nt; ++k) out[k] = vec[perm[k]];
-		vec.swap(out);
-	};
+	// new exon offsets (sequential prefix), then the gathers split over a few host threads by output range
 	std::vector<long long> off(nt + 1);
-	std::vector<int> es(st.r_exon_start.size()), ee(st.r_exon_end.size());
-	long long e = 0;
-	for (size_t k = 0; k < nt; ++k) {
-		long long s0 = st.r_exon_off[perm[k]], s1 = st.r_exon_off[perm[k] + 1];
-		off[k] = e;
-		for (long long q = s0; q < s1; ++q, ++e) {
-			es[(size_t)e] = st.r_exon_start[(size_t)q];
-			ee[(size_t)e] = st.r_exon_end[(size_t)q];
+	{
+		long long e = 0;
+		for (size_t k = 0; k < nt; ++k) {
+			off[k] = e;
+			e += st.r_exon_off[perm[k] + 1] - st.r_exon_off[perm[k]];
 		}
+		off[nt] = e;
 	}
-	off[nt] = e;
+	std::vector<int> comp(nt), sample(nt), chr(nt), gene(nt), es(st.r_exon_start.size()), ee(st.r_exon_end.size());
+	std::vector<int8_t> strand(nt);
+	std::vector<double> fpkm(nt), cov(nt);
+	auto work = [&](size_t k0, size_t k1) {
+		for (size_t k = k0; k < k1; ++k) {
+			size_t p = perm[k];
+			comp[k] = st.r_comp[p];
+			sample[k] = st.r_sample[p];
+			chr[k] = st.r_chr[p];
+			gene[k] = st.r_gene[p];
+			strand[k] = st.r_strand[p];
+			fpkm[k] = st.r_fpkm[p];
+			cov[k] = st.r_cov[p];
+			long long s0 = st.r_exon_off[p], s1 = st.r_exon_off[p + 1], e = off[k];
+			for (long long q = s0; q < s1; ++q, ++e) {
+				es[(size_t)e] = st.r_exon_start[(size_t)q];
+				ee[(size_t)e] = st.r_exon_end[(size_t)q];
+			}
+		}
+	};
+	size_t nThreads = nt >= 65536 ? 4 : 1;
+	if (const char *e = getenv("PSC_MERGE_THREADS")) nThreads = (size_t)std::max(1, atoi(e)); // tests
+	if (nThreads > nt) nThreads = 1;
+	std::vector<std::thread> pool;
+	for (size_t t = 1; t < nThreads; ++t) pool.emplace_back(work, nt * t / nThreads, nt * (t + 1) / nThreads);
+	work(0, nt / nThreads);
+	for (auto &th : pool) th.join();
 	st.r_exon_off.swap(off);
 	st.r_exon_start.swap(es);
 	st.r_exon_end.swap(ee);
-	gather(st.r_comp);
-	gather(st.r_sample);
-	gather(st.r_chr);
-	gather(st.r_gene);
-	gather(st.r_strand);
-	gather(st.r_fpkm);
-	gather(st.r_cov);
+	st.r_comp.swap(comp);
+	st.r_sample.swap(sample);
+	st.r_chr.swap(chr);
+	st.r_gene.swap(gene);
+	st.r_strand.swap(strand);
+	st.r_fpkm.swap(fpkm);
+	st.r_cov.swap(cov);
 }
 
 static int launch_grid(psc_ctx *ctx, long long units)

@@ -33,6 +33,9 @@ def test_two_pass_schedule_keeps_component_major_output(monkeypatch):
     wl = testkit.Workload.synth(seed=42, n_genes=30, n_samples=4, mean_pairs=200.0, exon_mu=2.2, iso_lambda=4.0, p_alt=0.3, p_ir=0.1, threads=4)
     rep = wl.check(testkit.SHIM_PATH, coop=1)
     assert rep.passed, rep.summary()
+    monkeypatch.setenv("PSC_MERGE_THREADS", "3")  # the host-side merge of the two lists, multi-threaded
+    rep = wl.check(testkit.SHIM_PATH, coop=1)
+    assert rep.passed, rep.summary()
 
 
 @pytest.mark.parametrize("force_overlap", [False, True])
