@@ -151,6 +151,10 @@ int psc_get_timing(psc_ctx *ctx, psc_timing *out);
  * unit; used by the tests to cross-check the warp-cooperative code paths). */
 int psc_set_coop_width(psc_ctx *ctx, int32_t width);
 
+/* Diagnostic: y[i] = the device's pow(x[i], 0.25) as ComputeScore (TranscriptDecider.hpp:394-401) evaluates it,
+ * x in (0.1, 1].  The tests compare it with the host libm, whose rounding the engine reproduces bit for bit. */
+int psc_debug_pow_quarter(psc_ctx *ctx, const double *x, double *y, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,7 +70,7 @@ class psc_timing(C.Structure):
 SYMBOLS = ["psc_create", "psc_destroy", "psc_last_error", "psc_set_params", "psc_set_graph", "psc_set_reads",
            "psc_build_constraints", "psc_constraint_counts", "psc_get_constraint_table", "psc_solve",
            "psc_transcript_counts", "psc_get_transcripts", "psc_get_comp_stats", "psc_get_timing",
-           "psc_set_coop_width"]
+           "psc_set_coop_width", "psc_debug_pow_quarter"]
 
 
 def load(path=None):
@@ -100,6 +100,7 @@ def load(path=None):
     lib.psc_get_comp_stats.argtypes = [vp, C.POINTER(psc_comp_stats)]
     lib.psc_get_timing.argtypes = [vp, C.POINTER(psc_timing)]
     lib.psc_set_coop_width.argtypes = [vp, C.c_int32]
+    lib.psc_debug_pow_quarter.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64]
     for name in SYMBOLS:
         if name not in ("psc_destroy", "psc_last_error"):
             getattr(lib, name).restype = C.c_int

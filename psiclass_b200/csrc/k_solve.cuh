@@ -6,6 +6,7 @@
 // carved out of per-unit scratch arenas in HBM that the host sizes from the table sizes.
 #pragma once
 #include "psc_internal.h"
+#include "pow_quarter.h"
 
 namespace pscdev {
 
@@ -431,23 +432,13 @@ PSC_DEV void enumerate_candidates(const Coop &co, const GraphDev &g, const Solve
 // =============================================================================================
 // shared helpers of the per-sample phases
 // =============================================================================================
-// x^(1/4) for x in (0.1, 1], the only transcendental on the path (the reference calls pow(x, 0.25)).
-// CUDA's pow is allowed 2 ulp and differs from the host libm often enough to flip a near-tie in the set
-// cover on roughly one workload in thirty (tools/gpu_fuzz.py).  This routine is CORRECTLY ROUNDED:
-// sqrt(sqrt(x)) is within an ulp, and one Newton step on y^4 = x with the residual taken in double-double
-// (error-free products through fma) lands on the nearest double (checked on the host against 128-bit
-// arithmetic: 0 misroundings in 2e7 samples).  glibc 2.39's pow (0.54 ulp bound) returns the same value in
-// 99.9 % of the calls; matching its remaining misroundings would take a port of its log/exp tables.
+// pow(x, 0.25) of ComputeScore: the device evaluates the host libm's own algorithm (pow_quarter.h), bit for bit
 PSC_DEV double pow_quarter(double x)
 {
 #ifdef PSC_CPU_SHIM
 	return pow(x, 0.25); // the shim is compared with the oracle, which calls the host libm like the reference
 #else
-	double r = sqrt(sqrt(x));
-	double r2h = r * r, r2l = __fma_rn(r, r, -r2h);
-	double r4h = r2h * r2h, r4l = __fma_rn(r2h, r2h, -r4h);
-	double resid = ((x - r4h) - r4l) - 2 * r2h * r2l;
-	return r + resid / (4 * r2h * r);
+	return pow_quarter_libm(x);
 #endif
 }
 

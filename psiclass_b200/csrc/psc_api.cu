@@ -92,6 +92,16 @@ struct DevBuf {
 
 #include "psc_solve_state.h"
 
+__global__ void k_pow_quarter(const double *x, double *y, long long n)
+{
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#ifdef PSC_CPU_SHIM
+	for (i = 0; i < n; ++i) y[i] = pscdev::pow_quarter(x[i]);
+#else
+	if (i < n) y[i] = pscdev::pow_quarter(x[i]);
+#endif
+}
+
 struct SampleState {
 	SampleDev d;
 	bool loaded = false;
@@ -267,6 +277,22 @@ int psc_set_coop_width(psc_ctx *ctx, int32_t width)
 	width = 1;
 #endif
 	ctx->coop = width;
+	return 0;
+}
+
+int psc_debug_pow_quarter(psc_ctx *ctx, const double *x, double *y, int64_t n)
+{
+	cudaSetDevice(ctx->device);
+	if (n <= 0) return 0;
+	DevBuf dx, dy;
+	if (!dx.ensure(sizeof(double) * (size_t)n) || !dy.ensure(sizeof(double) * (size_t)n)) return ctx->fail("out of device memory");
+	CK(cudaMemcpyAsync(dx.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+	PSC_LAUNCH(k_pow_quarter, (int)((n + 255) / 256), 256, ctx->stream, dx.as<double>(), dy.as<double>(), (long long)n);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(y, dy.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	dx.release();
+	dy.release();
 	return 0;
 }
 

@@ -65,10 +65,30 @@ def test_chunked_scratch_budget_matches_oracle(monkeypatch, force_overlap):
     assert rep.passed, rep.summary()
 
 
+def test_device_pow_quarter_is_bit_identical_to_host_libm():
+    """The one transcendental of the path, evaluated on the device, against libm's pow."""
+    import ctypes as C
+    import ctypes.util
+    import numpy as np
+    rng = np.random.default_rng(7)
+    n = 4_000_000
+    x = np.concatenate([0.1 + 0.9 * rng.random(n // 2), rng.integers(1, 100000, n // 2) / (rng.integers(1, 100000, n // 2) * 1.0)])
+    x = x[(x > 0.1) & (x <= 1.0)].copy()
+    y = np.empty_like(x)
+    eng = abi.Engine(0)
+    eng.call("psc_debug_pow_quarter", x.ctypes.data_as(C.POINTER(C.c_double)), y.ctypes.data_as(C.POINTER(C.c_double)), len(x))
+    libm = C.CDLL(ctypes.util.find_library("m"))
+    libm.pow.restype = C.c_double
+    libm.pow.argtypes = [C.c_double, C.c_double]
+    sample = rng.choice(len(x), 300000, replace=False)
+    bad = sum(1 for i in sample if libm.pow(float(x[i]), 0.25) != float(y[i]))
+    assert bad == 0, "%d of %d results differ from the host libm" % (bad, len(sample))
+
+
 def test_score_near_tie_is_decided_like_the_host_libm():
     """Found by tools/gpu_fuzz.py: with CUDA's 2-ulp pow() the set cover of one unit of this workload took
     the other side of a near-tie in ComputeScore and four abundances came out 1e-3 off.  The engine now
-    uses a correctly rounded x^(1/4) (k_solve.cuh: pow_quarter)."""
+    evaluates the host libm's own pow algorithm (pow_quarter.h)."""
     wl = testkit.Workload.synth(threads=8, seed=2020, n_genes=150, n_samples=3, mean_pairs=400.0, exon_mu=2.0, iso_lambda=3.0,
                                 p_alt=0.3, p_ir=0.1, p_noise=0.0, p_overlap=0.0, single_end=0, stranded=0)
     rep = wl.check(abi.LIB_PATH, coop=32)

@@ -49,6 +49,15 @@ def test_chunked_scratch_budget_gives_the_same_answer(monkeypatch, force_overlap
     assert rep.passed, rep.summary()
 
 
+def test_device_pow_algorithm_equals_host_libm(tmp_path):
+    """ComputeScore's pow(x, 0.25) is the path's only transcendental; the device evaluates the host libm's own
+    algorithm (psiclass_b200/csrc/pow_quarter.h).  Compiled for the host it must equal pow() on every input."""
+    exe = str(tmp_path / "pow_check")
+    run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "pow_check.cpp")])
+    out = run([exe, "20000000"])
+    assert "mismatches 0" in out, out
+
+
 def test_unlimited_dp_constraints_and_paralog_flag():
     wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=4)
     assert wl.check(testkit.SHIM_PATH, coop=1, max_dp=-1).passed
