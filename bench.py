@@ -325,8 +325,8 @@ def main():
         alg = kbytes[dom] / launches_per_step
         achieved = (alg / 1e9) / (per_launch_ms / 1e3) if per_launch_ms > 0 and alg > 0 else 0.0
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one `ncu --set full` capture of the
-        # default workload (profiles/r1_ncu_summary.md): the launch over the heavy DP components, 40.0 + 185.2 MB
-        traffic = 225.2e6 if (names[dom] == "dp_units" and not a.genes) else None
+        # default workload (profiles/r1_ncu_summary.md): the launch over the heavy DP components, 37.8 + 169.8 MB
+        traffic = 207.6e6 if (names[dom] == "dp_units" and not a.genes) else None
         line = {
             "metric": METRIC, "value": total_components * a.steps / wall_max, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * wall_max / a.steps,
