@@ -728,9 +728,12 @@ PSC_DEV int dp_coalesce(DpState &st, uint64_t *cb, int *cf, int *cl, int A)
 	for (int i = co.lane; i < A; i += co.n) d.sortidx[i] = i;
 	co.sync();
 	coop_sort(co, d.sortidx, A, [&](int a, int b) {
-		if (tx_row_less(cb + (long long)a * W, cf[a], cb + (long long)b * W, cf[b], W)) return true;
-		if (tx_row_less(cb + (long long)b * W, cf[b], cb + (long long)a * W, cf[a], W)) return false;
-		return a < b;
+		int fa = cf[a], fb = cf[b];
+		if (fa != fb) return fa < fb;
+		const uint64_t *ra = cb + (long long)a * W, *rb = cb + (long long)b * W;
+		for (int w = 0; w < W; ++w)
+			if (ra[w] != rb[w]) return brev64(ra[w]) > brev64(rb[w]); // CompSortTranscripts, see tx_row_less
+		return a < b; // equal rows: keep the order of arrival
 	});
 	// unique rows -> second buffer, then back
 	int K = 0;

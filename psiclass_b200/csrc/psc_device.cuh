@@ -232,10 +232,11 @@ template <class Less> PSC_DEV void coop_sort(const Coop &co, int *idx, int n, Le
 				if (l > i) {
 					int a = idx[i], b = idx[l];
 					bool up = (i & k) == 0;
-					// a > b  <=>  less(b, a); -1 is +inf
-					bool a_gt_b = (a < 0) ? (b >= 0) : (b < 0 ? false : less(b, a));
-					bool b_gt_a = (b < 0) ? (a >= 0) : (a < 0 ? false : less(a, b));
-					if (up ? a_gt_b : b_gt_a) {
+					// ascending pair: swap if a > b; descending pair: swap if b > a.  One comparator call either way
+					// (x > y  <=>  less(y, x); -1 is +inf)
+					int x = up ? a : b, y = up ? b : a;
+					bool x_gt_y = (x < 0) ? (y >= 0) : (y < 0 ? false : less(y, x));
+					if (x_gt_y) {
 						idx[i] = b;
 						idx[l] = a;
 					}
