@@ -227,9 +227,11 @@ template <class Less> PSC_DEV void coop_sort(const Coop &co, int *idx, int n, Le
 	co.sync();
 	for (int k = 2; k <= P; k <<= 1) {
 		for (int j = k >> 1; j > 0; j >>= 1) {
-			for (int i = co.lane; i < P; i += co.n) {
-				int l = i ^ j;
-				if (l > i) {
+			// one compare-exchange per lane and step: pair t works on (i, i | j), i = t with a 0 inserted at bit log2(j)
+			for (int t = co.lane; t < (P >> 1); t += co.n) {
+				int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+				int l = i | j;
+				{
 					int a = idx[i], b = idx[l];
 					bool up = (i & k) == 0;
 					// ascending pair: swap if a > b; descending pair: swap if b > a.  One comparator call either way
