@@ -95,6 +95,27 @@ def test_score_near_tie_is_decided_like_the_host_libm():
     assert rep.passed, rep.summary()
 
 
+@pytest.mark.parametrize("seed", [9001, 9002, 9003, 9004, 9005, 9006])
+def test_randomised_workload_shapes(seed, monkeypatch):
+    """A slice of tools/gpu_fuzz.py: random layout (single/paired end, strandedness, noise, isoform density,
+    depth) under a random schedule (plain, two streams, chunked scratch)."""
+    import random
+    rng = random.Random(seed)
+    cfg = dict(seed=seed, n_genes=rng.choice([40, 80, 150]), n_samples=rng.choice([2, 3, 5, 8]),
+               mean_pairs=rng.choice([5.0, 40.0, 150.0, 400.0]), exon_mu=rng.choice([1.6, 2.0, 2.4]),
+               iso_lambda=rng.choice([1.5, 3.0, 5.0]), p_alt=rng.choice([0.1, 0.3, 0.45]), p_ir=rng.choice([0.0, 0.1]),
+               p_noise=rng.choice([0.0, 0.1]), p_overlap=rng.choice([0.0, 0.15]), single_end=rng.choice([0, 0, 1]),
+               stranded=rng.choice([0, 1]))
+    mode = rng.choice(["plain", "overlap", "chunks", "overlap+chunks"])
+    if "overlap" in mode:
+        monkeypatch.setenv("PSC_FORCE_OVERLAP", "1")
+    if "chunks" in mode:
+        monkeypatch.setenv("PSC_MEM_BUDGET_MB", "4")
+    wl = testkit.Workload.synth(threads=8, **cfg)
+    rep = wl.check(abi.LIB_PATH, coop=32)
+    assert rep.passed, "%s %s: %s" % (cfg, mode, rep.summary())
+
+
 def test_flags_unlimited_dp_and_primary_paralog():
     wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=8)
     assert wl.check(abi.LIB_PATH, max_dp=-1).passed
