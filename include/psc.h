@@ -140,7 +140,7 @@ typedef struct psc_timing {
 	/* per-kernel device time (CUDA events around every launch, summed) and launch counts of the last
 	 * psc_build_constraints + psc_solve: 0 group_ranges, 1 build_constraints, 2 prologue,
 	 * 3 enumerate, 4 dp_units, 5 units phase 1 (pick round 1), 6 emit, 7 dp_merge,
-	 * 8 units phase 2 (pick round 2, refine, EM), 9 units phase 3 (rescue) */
+	 * 8 units phase 2 (pick round 2, refine, EM), 9 units phase 3 (rescue), 10 dp2_units (static-program DP) */
 	double kernel_ms[12];
 	int64_t kernel_count[12];
 	int64_t kernel_bytes[12]; /* algorithmic bytes attributed to the kernel, 0 if not modelled */

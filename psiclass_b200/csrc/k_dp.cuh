@@ -131,6 +131,7 @@ struct DpState {
 	double minAbundance;
 	int timeStamp, epoch, iter;
 	int *err;
+	struct Dp2 *z; // static-program engine (k_dp2.cuh), null for the walk engine
 	bool prof; // PSC_DEBUG_DP: per-mode cycle counters
 	mutable long long nStates, nLevels, nIters, nFrames, nRoots, cycRoot, cycAssign; // instrumentation (PSC_DEBUG_DP)
 };
@@ -491,6 +492,15 @@ PSC_DEV void dp_sort_ext(const DpState &st, int *src, int extCnt, bool hasRoom)
 } // namespace pscdev
 #include "k_dp_walk.cuh"
 namespace pscdev {
+// what dp_pick needs from a SolveSubTranscript engine: the result of one root call
+struct DpRootRes {
+	double cover;
+	const uint64_t *bits;
+	int first, last;
+};
+} // namespace pscdev
+#include "k_dp2.cuh"
+namespace pscdev {
 
 
 // copy a memo entry into one of the two "best so far" registers kept in work[] (SetDpContent)
@@ -510,9 +520,24 @@ PSC_DEV void dp_take(const DpState &st, DpBest &dst, const uint64_t *bits, doubl
 	st.co.sync();
 }
 
+// the iterative walk with the f1/f2/hash memo (k_dp_walk.cuh)
+struct DpEngineWalk {
+	static PSC_DEV DpRootRes root(DpState &st, int i)
+	{
+		long long r = dp_solve_root(st, i);
+		DpRootRes o;
+		o.cover = st.d.ent[r].cover;
+		o.bits = st.d.ebits + r * st.W;
+		o.first = st.d.ent[r].first;
+		o.last = st.d.ent[r].last;
+		return o;
+	}
+	static PSC_DEV void abundances_changed(DpState &) {}
+};
+
 // PickTranscriptsByDP (TranscriptDecider.cpp:860-1201) on the constraints currently loaded in
 // st.d.tc*; the new transcripts are appended to st.d.tx* and their count returned.
-PSC_DEVN int dp_pick(DpState &st, int iterBound)
+template <class Engine> PSC_DEVN int dp_pick(DpState &st, int iterBound)
 {
 	const Coop &co = st.co;
 	const CompView &v = st.v;
@@ -560,9 +585,9 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 	for (int i = 0; i < n; ++i)
 		if (st.cs[i]) {
 			long long tq = st.prof ? clock64() : 0;
-			long long r = dp_solve_root(st, i);
+			DpRootRes r = Engine::root(st, i);
 			if (st.prof) st.cycRoot += clock64() - tq;
-			double c = d.ent[r].cover;
+			double c = r.cover;
 			if (c > maxAbundance) maxAbundance = c;
 		}
 	st.forAbundance = false;
@@ -595,10 +620,10 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 				for (int i = 0; i < n; ++i) {
 					if (!st.cs[i]) continue;
 					long long tq = st.prof ? clock64() : 0;
-					long long r = dp_solve_root(st, i);
+					DpRootRes r = Engine::root(st, i);
 					if (st.prof) st.cycRoot += clock64() - tq;
-					double c = d.ent[r].cover;
-					if (c > maxCover.cover && c > 0) dp_take(st, maxCover, d.ebits + r * W, c, d.ent[r].first, d.ent[r].last);
+					double c = r.cover;
+					if (c > maxCover.cover && c > 0) dp_take(st, maxCover, r.bits, c, r.first, r.last);
 				}
 				if (maxCover.cover == -1) break;
 				int slot = -1;
@@ -681,6 +706,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 		} else
 			*st.err = 23;
 		// subtract; a constraint that runs dry invalidates the cached paths containing it
+		bool ranDry = false;
 		for (int q = 0; q < coveredCnt; ++q) {
 			int j = d.covered[q];
 			double ab = d.tcab[j];
@@ -688,6 +714,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 				double tmp = ab > update ? update : ab;
 				ab -= tmp;
 				if (ab <= 0) {
+					ranDry = true;
 					for (int k = co.lane; k < d.cCap; k += co.n)
 						if (d.cvalid[k] && compat(d.cbits + (long long)k * W, d.cent[k].first, d.cent[k].last, false,
 						                          d.tcb + (long long)j * W, d.tcf[j], d.tcl[j], W) == 1)
@@ -699,6 +726,7 @@ PSC_DEVN int dp_pick(DpState &st, int iterBound)
 			if (co.lane == 0) d.tcab[j] = ab;
 			co.sync();
 		}
+		if (ranDry) Engine::abundances_changed(st);
 		st.cycAssign += clock64() - tqa;
 		++iterCnt;
 		++st.nIters;
@@ -882,6 +910,45 @@ PSC_DEV void dp_use_shared(DpScratch &d, int n, int W, char *sm, size_t smBytes)
 	d.work = work;
 }
 
+// the constraints PickTranscriptsByDP sees: truncated to their first maxDp subexons
+// (TruncateConstraintsCoverFrom, Constraints.hpp:400-434) or every stride-th one
+// (DownsampleConstraintsFrom, Constraints.hpp:362-398)
+PSC_DEV void dp_load_constraints(DpState &st, const TableView &t, int unitStride, int maxDp)
+{
+	const Coop &co = st.co;
+	const int W = st.W;
+	if (maxDp > 0) {
+		// TruncateConstraintsCoverFrom (Constraints.hpp:400-434)
+		for (int k = co.lane; k < t.C; k += co.n) {
+			const uint64_t *src = t.bits + (long long)k * W;
+			uint64_t *dst = st.d.tcb + (long long)k * W;
+			for (int w = 0; w < W; ++w) dst[w] = 0;
+			int taken = 0, last = t.first[k];
+			for (int q = t.first[k]; q <= t.last[k] && taken < maxDp; ++q)
+				if (bt_test(src, q)) { bt_set(dst, q); last = q; ++taken; }
+			st.d.tcf[k] = t.first[k];
+			st.d.tcl[k] = last;
+			st.d.tcsup[k] = t.support[k];
+			st.d.tcnorm[k] = t.norm[k];
+			st.d.tcab[k] = t.norm[k];
+		}
+		st.d.tcCnt = t.C;
+	} else {
+		int stride = unitStride > 0 ? unitStride : 1; // DownsampleConstraintsFrom (Constraints.hpp:362-398)
+		int cnt = (t.C + stride - 1) / stride;
+		for (int k = co.lane; k < cnt; k += co.n) {
+			int src = k * stride;
+			for (int w = 0; w < W; ++w) st.d.tcb[(long long)k * W + w] = t.bits[(long long)src * W + w];
+			st.d.tcf[k] = t.first[src];
+			st.d.tcl[k] = t.last[src];
+			st.d.tcsup[k] = t.support[src];
+			st.d.tcnorm[k] = t.norm[src];
+			st.d.tcab[k] = t.norm[src];
+		}
+		st.d.tcCnt = cnt;
+	}
+}
+
 PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv, const DpUnit &u, char *scratchBase,
                            char *txBase, int *n_tx_out, char *sm, size_t smBytes, long long *dbg)
 {
@@ -914,49 +981,76 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 	st.epoch = 0;
 	st.prof = dbg != nullptr;
 	st.err = sv.error_flag;
+	st.z = nullptr;
 	st.forAbundance = false;
 	st.minAbundance = 0;
 	st.timeStamp = 0;
-	int W = v.W;
-	int maxDp = sv.prm.maxDpConstraintSize;
-	if (maxDp > 0) {
-		// TruncateConstraintsCoverFrom (Constraints.hpp:400-434)
-		for (int k = co.lane; k < t.C; k += co.n) {
-			const uint64_t *src = t.bits + (long long)k * W;
-			uint64_t *dst = st.d.tcb + (long long)k * W;
-			for (int w = 0; w < W; ++w) dst[w] = 0;
-			int taken = 0, last = t.first[k];
-			for (int q = t.first[k]; q <= t.last[k] && taken < maxDp; ++q)
-				if (bt_test(src, q)) { bt_set(dst, q); last = q; ++taken; }
-			st.d.tcf[k] = t.first[k];
-			st.d.tcl[k] = last;
-			st.d.tcsup[k] = t.support[k];
-			st.d.tcnorm[k] = t.norm[k];
-			st.d.tcab[k] = t.norm[k];
-		}
-		st.d.tcCnt = t.C;
-	} else {
-		int stride = u.stride > 0 ? u.stride : 1; // DownsampleConstraintsFrom (Constraints.hpp:362-398)
-		int cnt = (t.C + stride - 1) / stride;
-		for (int k = co.lane; k < cnt; k += co.n) {
-			int src = k * stride;
-			for (int w = 0; w < W; ++w) st.d.tcb[(long long)k * W + w] = t.bits[(long long)src * W + w];
-			st.d.tcf[k] = t.first[src];
-			st.d.tcl[k] = t.last[src];
-			st.d.tcsup[k] = t.support[src];
-			st.d.tcnorm[k] = t.norm[src];
-			st.d.tcab[k] = t.norm[src];
-		}
-		st.d.tcCnt = cnt;
-	}
+	dp_load_constraints(st, t, u.stride, sv.prm.maxDpConstraintSize);
 	co.sync();
-	int nt = dp_pick(st, u.iterBound);
+	int nt = dp_pick<DpEngineWalk>(st, u.iterBound);
 	if (co.lane == 0) *n_tx_out = nt;
 	if (dbg && co.lane == 0) {
 		dbg[0] = clock64() - t0;
 		dbg[1] = st.nStates + ((st.cycRoot >> 20) << 32);
 		dbg[2] = st.nLevels + ((st.cycAssign >> 20) << 32);
 		dbg[3] = st.nIters + (st.nFrames << 12) + (st.nRoots << 40);
+	}
+	co.sync();
+}
+
+// The same unit on the static-program engine (k_dp2.cuh).  `arena` is the calling group's private working set of
+// arenaBytes; a unit whose key / frame / list tables outgrow it reports *n_tx_out = -1 and is redone by the walk engine.
+PSC_DEVN void dp2_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv, const DpUnit &u, char *arena, size_t arenaBytes,
+                            char *txBase, int *n_tx_out, long long *dbg)
+{
+	DpState st;
+	st.nStates = st.nLevels = st.nIters = st.nFrames = st.nRoots = st.cycRoot = st.cycAssign = 0;
+	long long t0 = clock64();
+	st.co = co;
+	st.v = comp_view(g, u.comp);
+	const CompView &v = st.v;
+	int E = v.noff[v.n] - v.noff[0];
+	TableView t = table_view(sv.samples[u.sample], u.comp);
+	int Ccap = t.C > 100 ? t.C : 100;
+	Dp2 z;
+	size_t used = dp2_layout(&st.d, &z, arena, v.n, E, Ccap, arenaBytes);
+	if (used > arenaBytes || z.maxKeys < 8) { // does not even hold the fixed part
+		if (co.lane == 0) *n_tx_out = -1;
+		co.sync();
+		return;
+	}
+	for (int k = co.lane; k < v.n + 1; k += co.n) z.key1[k] = -1;
+	for (int k = co.lane; k < z.hashCap; k += co.n) z.khash[k] = -1;
+	DpTxList out;
+	dp_txlist_layout(&out, txBase + u.tx_off, u.iterBound, v.W);
+	st.d.txb = out.b;
+	st.d.txf = out.f;
+	st.d.txl = out.l;
+	st.d.txCap = u.iterBound;
+	st.cs = sv.can_start + v.base;
+	st.ce = sv.can_end + v.base;
+	st.W = v.W;
+	st.epoch = 0;
+	st.prof = dbg != nullptr;
+	st.err = sv.error_flag;
+	st.z = &z;
+	st.forAbundance = false;
+	st.minAbundance = 0;
+	st.timeStamp = 0;
+	dp_load_constraints(st, t, u.stride, sv.prm.maxDpConstraintSize);
+	co.sync();
+	int nt = dp_pick<DpEngineProgram>(st, u.iterBound);
+	if (z.overflow) nt = -1;
+	if (co.lane == 0) *n_tx_out = nt;
+	if (dbg && co.lane == 0) {
+		dbg[0] = clock64() - t0;
+		dbg[1] = st.nStates + ((st.cycRoot >> 20) << 32);
+		dbg[2] = st.nLevels + ((st.cycAssign >> 20) << 32);
+		dbg[3] = st.nIters + (st.nFrames << 12) + (st.nRoots << 40);
+		dbg[4] = z.nKeys;
+		dbg[5] = z.nFrames;
+		dbg[6] = z.nList;
+		dbg[7] = z.overflow ? -1 : z.maxKeys;
 	}
 	co.sync();
 }

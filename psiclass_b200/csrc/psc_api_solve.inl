@@ -70,6 +70,30 @@ __global__ void __launch_bounds__(128, PSC_DP_MINBLOCKS) k_dp_units(GraphDev g, 
 	}
 }
 
+// The static-program DP engine (k_dp2.cuh): every cooperative group of the grid owns one arena of arenaBytes and
+// pulls (component, sample) units, heaviest first.  Units that outgrow their arena report n_tx = -1 and are counted
+// in *overflow; the host redoes them with k_dp_units.
+#ifndef PSC_DP2_MINBLOCKS
+#define PSC_DP2_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, PSC_DP2_MINBLOCKS) k_dp2_units(GraphDev g, SolveDev sv, const DpUnit *units, const int *order, int nUnits,
+                                                                    char *arenas, size_t arenaBytes, char *txArena, int *n_tx, int *counter,
+                                                                    int *overflow, int width, long long *dbg)
+{
+	Coop co = make_coop(width);
+	char *arena = arenas + (size_t)coop_id(width) * arenaBytes;
+	for (;;) {
+		int u = 0;
+		if (co.lane == 0) u = atomic_add(counter, 1);
+		u = co.bcast(u, 0);
+		if (u >= nUnits) break;
+		int ui = order[u];
+		dp2_unit_pick(co, g, sv, units[ui], arena, arenaBytes, txArena, n_tx + ui, dbg ? dbg + 8 * (long long)ui : nullptr);
+		if (co.lane == 0 && n_tx[ui] < 0) atomic_add(overflow, 1);
+		co.sync();
+	}
+}
+
 __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const DpUnit *units, const int *compList, int nComp,
                                                   const int *n_tx, const char *txArena, char *scratch, const long long *scr_off,
                                                   int *counter, int width)
@@ -282,7 +306,6 @@ int psc_solve(psc_ctx *ctx)
 			int W = (n + 63) / 64;
 			long long cap;
 			if (st.h_use_dp[(size_t)c]) {
-				if (n > 10000) return ctx->fail("component with more than 10000 subexons on the DP path is not supported");
 				int Cmax = 0;
 				for (int s = 0; s < S; ++s) Cmax = std::max(Cmax, ctx->samples[(size_t)s].h_ncon[(size_t)c]);
 				cap = 1000 + (long long)Cmax + 100LL * (S - 1) + 8;
@@ -500,135 +523,245 @@ int psc_solve(psc_ctx *ctx)
 	lap("enumerate");
 	// ---- P2b: DP.  Units are (component, sample); chunks of components that fit the memory budget ----
 	long long dpBytes = 0;
-	auto run_dp = [&](const std::vector<int> &comps, cudaStream_t strm, DpBufs &db, int *cnt, bool wait) -> int {
-			size_t i0 = 0;
-			while (i0 < comps.size()) {
-				std::vector<DpUnit> units;
-				std::vector<long long> mergeOff, cost;
-				long long sAcc = 0, tAcc = 0, mAcc = 0;
-				size_t i1 = i0;
-				while (i1 < comps.size()) {
-					int c = comps[i1];
-					int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
-					int W = (n + 63) / 64;
-					long long cap = rowOff[(size_t)c + 1] - rowOff[(size_t)c];
-					// the reference visits the samples in descending number of constraints (qsort ascending,
-					// stable, walked from the back: Q11)
-					std::vector<int> ord((size_t)S);
-					for (int s = 0; s < S; ++s) ord[(size_t)s] = s;
-					std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-						return ctx->samples[(size_t)a].h_ncon[(size_t)c] < ctx->samples[(size_t)b].h_ncon[(size_t)c];
-					});
-					std::vector<DpUnit> mine;
-					long long sNeed = 0, tNeed = 0;
-					int downsampleCnt = -1;
-					for (int oi = S - 1; oi >= 0; --oi) {
-						int s = ord[(size_t)oi];
-						int C = ctx->samples[(size_t)s].h_ncon[(size_t)c], M = ctx->samples[(size_t)s].h_npair[(size_t)c];
-						DpUnit u;
-						u.comp = c;
-						u.sample = s;
-						u.iterBound = oi == S - 1 ? C : 100;
-						u.stride = 0;
-						if (ctx->prm.max_dp_constraint_size <= 0) {
-							bool down = (C > 1000 && (long long)C * 10 < M) || (downsampleCnt > 0 && C >= downsampleCnt) || n >= 1500;
-							if (down) { // TranscriptDecider.cpp:3214-3227
-								int stride = C > 0 ? M / C : 1;
-								if (downsampleCnt > 0) stride = C / downsampleCnt;
-								if (stride < 1) stride = 1;
-								u.stride = stride;
-								if (downsampleCnt <= 0) downsampleCnt = (C + stride - 1) / stride;
-							}
-						}
-						if (u.iterBound < 1) u.iterBound = 1;
-						u.scratch_off = sAcc + sNeed;
-						u.tx_off = tAcc + tNeed;
-						sNeed += (long long)dp_scratch_layout(nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100), 1);
-						tNeed += (long long)dp_txlist_layout(nullptr, nullptr, u.iterBound, W);
-						mine.push_back(u);
-					}
-					if (i1 > i0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
-					for (auto &u : mine) {
-						// algorithmic bytes of the DP kernel: the sample's constraint table read once, its transcript list written once
-						dpBytes += (long long)ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] * (8LL * W + 40) + (long long)u.iterBound * (8LL * W + 8);
-						units.push_back(u);
-						cost.push_back((long long)u.iterBound * (ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] + 1));
-					}
-					sAcc += sNeed;
-					tAcc += tNeed;
-					mergeOff.push_back(mAcc);
-					mAcc += (long long)dp_merge_layout(nullptr, nullptr, W, cap);
-					++i1;
-				}
-				// note: the offsets of the units we rolled back (mine, on break) were never committed
-				int nUnits = (int)units.size(), nComp = (int)(i1 - i0);
-				std::vector<int> order((size_t)nUnits);
-				for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
-				std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
-				if (!(*db.scratch).ensure((size_t)std::max(sAcc, mAcc) + 16) || !db.dp_tx.ensure((size_t)tAcc + 16) ||
-				    !db.dp_ntx.ensure(sizeof(int) * (size_t)(nUnits + 1)))
-					return ctx->fail("out of device memory (DP scratch)");
-				CK(cudaMemsetAsync(db.dp_ntx.p, 0, sizeof(int) * (size_t)(nUnits + 1), strm));
-				if (!upload(ctx, db.list, comps.data() + i0, (size_t)nComp, strm) || !upload(ctx, db.dp_units, units.data(), units.size(), strm) ||
-				    !upload(ctx, db.dp_order, order.data(), order.size(), strm) || !upload(ctx, db.dp_scr_off, mergeOff.data(), mergeOff.size(), strm))
-					return ctx->fail("out of device memory");
-				lap("dp host prep");
-				CK(cudaMemsetAsync(cnt, 0, 32, strm));
-				{
-					const int smemPerWarp = ctx->coop == 32 ? PSC_DP_SMEM_PER_WARP : 0; // x 4 warps per CTA, 2 CTAs per SM (255 registers)
-					long long *dbgPtr = nullptr;
-					const bool dbgOn = getenv("PSC_DEBUG_DP") != nullptr;
-					if (dbgOn) {
-						if (!st.dp_dbg.ensure(sizeof(long long) * 8 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
-						CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 8 * (size_t)(nUnits + 1), strm));
-						dbgPtr = st.dp_dbg.as<long long>();
-					}
-	#ifndef PSC_CPU_SHIM
-					CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PSC_DP_SMEM_PER_WARP));
-					ctx->ktime_begin(4, strm);
-					k_dp_units<<<launch_grid(ctx, nUnits), 128, 4 * smemPerWarp, strm>>>(
-					    ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits, (char *)(*db.scratch).p, (char *)db.dp_tx.p,
-					    db.dp_ntx.as<int>(), cnt, ctx->coop, smemPerWarp, dbgPtr);
-					ctx->ktime_end();
-	#else
-					KLAUNCH_ON(strm, 4, k_dp_units, launch_grid(ctx, nUnits), 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits,
-					        (char *)(*db.scratch).p, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, ctx->coop, smemPerWarp, dbgPtr);
-	#endif
-				}
-				++launches;
-				CK(cudaGetLastError());
-				CK(cudaMemsetAsync(cnt, 0, 32, strm));
-				KLAUNCH_ON(strm, 7, k_dp_merge, launch_grid(ctx, nComp), 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.list.as<int>(), nComp,
-				        db.dp_ntx.as<int>(), (const char *)db.dp_tx.p, (char *)(*db.scratch).p, db.dp_scr_off.as<long long>(), cnt, ctx->coop);
-				++launches;
-				CK(cudaGetLastError());
-				if (!wait && i1 == comps.size() && i0 == 0) return 0; // one chunk: the caller waits for it later
-				CK(cudaStreamSynchronize(strm));
-				lap("dp kernels");
-				if (getenv("PSC_DEBUG_DP")) {
-					std::vector<long long> h((size_t)nUnits * 8);
-					cudaMemcpy(h.data(), st.dp_dbg.p, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
-					std::vector<int> ix((size_t)nUnits);
-					for (int u = 0; u < nUnits; ++u) ix[(size_t)u] = u;
-					std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 8] > h[(size_t)b * 8]; });
-					long long tot = 0, totStates = 0, totFrames = 0;
-					for (int u = 0; u < nUnits; ++u) {
-						tot += h[(size_t)u * 8];
-						totStates += h[(size_t)u * 8 + 1] & 0xffffffff;
-						totFrames += (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff;
-					}
-					fprintf(stderr, "[dp] %d units, total %.1f Mcycles, %lld states, %lld frames\n", nUnits, tot / 1e6, totStates, totFrames);
-					for (int k = 0; k < 12 && k < nUnits; ++k) {
-						int u = ix[(size_t)k];
-						int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
-						fprintf(stderr, "[dp] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld\n", u, c, s,
-						        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
-						        h[(size_t)u * 8] / 1e6, h[(size_t)u * 8 + 1] & 0xffffffff, h[(size_t)u * 8 + 2] & 0xffffffff, h[(size_t)u * 8 + 3] & 0xfff, (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff, h[(size_t)u * 8 + 3] >> 40,
-						        h[(size_t)u * 8 + 1] >> 32, h[(size_t)u * 8 + 2] >> 32);
-					}
-				}
-				i0 = i1;
+	// One chunk of DP components in flight: dp_launch issues the static-program kernel asynchronously, dp_finish waits
+	// for it, redoes the units that overflowed their arena with the walk engine and launches the merge.
+	struct DpPending {
+		bool active = false;
+		std::vector<DpUnit> units;
+		std::vector<int> comps;
+		std::vector<long long> mergeOff;
+		long long mAcc = 0;
+		int nComp = 0;
+	};
+	const bool dpDbg = getenv("PSC_DEBUG_DP") != nullptr;
+	const bool useV2 = !(getenv("PSC_DP_V2") && atoi(getenv("PSC_DP_V2")) == 0);
+	auto dp_print = [&](const std::vector<DpUnit> &units, cudaStream_t strm, const char *what) {
+		int nUnits = (int)units.size();
+		CK(cudaStreamSynchronize(strm));
+		std::vector<long long> h((size_t)nUnits * 8);
+		cudaMemcpy(h.data(), st.dp_dbg.p, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+		std::vector<int> ix((size_t)nUnits);
+		for (int u = 0; u < nUnits; ++u) ix[(size_t)u] = u;
+		std::sort(ix.begin(), ix.end(), [&](int a, int b) { return h[(size_t)a * 8] > h[(size_t)b * 8]; });
+		long long tot = 0, totStates = 0, totFrames = 0, maxKeys = 0, maxFrames = 0, maxList = 0, nOvf = 0;
+		for (int u = 0; u < nUnits; ++u) {
+			tot += h[(size_t)u * 8];
+			totStates += h[(size_t)u * 8 + 1] & 0xffffffff;
+			totFrames += (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff;
+			maxKeys = std::max(maxKeys, h[(size_t)u * 8 + 4]);
+			maxFrames = std::max(maxFrames, h[(size_t)u * 8 + 5]);
+			maxList = std::max(maxList, h[(size_t)u * 8 + 6]);
+			if (h[(size_t)u * 8 + 7] < 0) ++nOvf;
+		}
+		fprintf(stderr, "[dp %s] %d units, total %.1f Mcycles, %lld states, %lld frames; program tables max keys %lld frames %lld list %lld, %lld overflowed\n",
+		        what, nUnits, tot / 1e6, totStates, totFrames, maxKeys, maxFrames, maxList, nOvf);
+		for (int k = 0; k < 12 && k < nUnits; ++k) {
+			int u = ix[(size_t)k];
+			int c = units[(size_t)u].comp, s = units[(size_t)u].sample;
+			fprintf(stderr, "[dp %s] unit %d comp %d sample %d n=%d C=%d iterBound=%d: %.1f Mcycles, states %lld levels %lld iters %lld frames %lld roots %lld | Mcyc in roots %lld, in assign %lld | keys %lld frames %lld list %lld cap %lld\n", what, u, c, s,
+			        ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c], ctx->samples[(size_t)s].h_ncon[(size_t)c], units[(size_t)u].iterBound,
+			        h[(size_t)u * 8] / 1e6, h[(size_t)u * 8 + 1] & 0xffffffff, h[(size_t)u * 8 + 2] & 0xffffffff, h[(size_t)u * 8 + 3] & 0xfff, (h[(size_t)u * 8 + 3] >> 12) & 0xfffffff, h[(size_t)u * 8 + 3] >> 40,
+			        h[(size_t)u * 8 + 1] >> 32, h[(size_t)u * 8 + 2] >> 32, h[(size_t)u * 8 + 4], h[(size_t)u * 8 + 5], h[(size_t)u * 8 + 6], h[(size_t)u * 8 + 7]);
+		}
+		return 0;
+	};
+	// redo the listed units with the walk engine, in sub-chunks whose scratch fits the budget
+	auto dp_walk_units = [&](DpPending &pd, const std::vector<int> &redo, cudaStream_t strm, DpBufs &db, int *cnt) -> int {
+		size_t k0 = 0;
+		while (k0 < redo.size()) {
+			long long sAcc = 0;
+			size_t k1 = k0;
+			std::vector<int> order;
+			std::vector<long long> cost;
+			while (k1 < redo.size()) {
+				DpUnit &u = pd.units[(size_t)redo[k1]];
+				int c = u.comp;
+				int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
+				if (n > 10000) return ctx->fail("component with more than 10000 subexons overflowed the DP program arena (raise PSC_MEM_BUDGET_MB)");
+				int C = ctx->samples[(size_t)u.sample].h_ncon[(size_t)c];
+				long long need = (long long)dp_scratch_layout(nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100), 1);
+				if (k1 > k0 && (size_t)(sAcc + need) > ctx->mem_budget) break;
+				u.scratch_off = sAcc;
+				sAcc += need;
+				order.push_back(redo[k1]);
+				cost.push_back((long long)u.iterBound * (C + 1));
+				++k1;
 			}
+			std::vector<int> ix(order.size());
+			for (size_t q = 0; q < ix.size(); ++q) ix[q] = (int)q;
+			std::stable_sort(ix.begin(), ix.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+			std::vector<int> sorted(order.size());
+			for (size_t q = 0; q < ix.size(); ++q) sorted[q] = order[(size_t)ix[q]];
+			if (!(*db.scratch).ensure((size_t)sAcc + 16) || !upload(ctx, db.dp_units, pd.units.data(), pd.units.size(), strm) ||
+			    !upload(ctx, db.dp_order, sorted.data(), sorted.size(), strm))
+				return ctx->fail("out of device memory (DP scratch)");
+			CK(cudaMemsetAsync(cnt, 0, 32, strm));
+			const int nRedo = (int)sorted.size();
+			const int smemPerWarp = ctx->coop == 32 ? PSC_DP_SMEM_PER_WARP : 0;
+			long long *dbgPtr = dpDbg ? st.dp_dbg.as<long long>() : nullptr;
+#ifndef PSC_CPU_SHIM
+			CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PSC_DP_SMEM_PER_WARP));
+			ctx->ktime_begin(4, strm);
+			k_dp_units<<<launch_grid(ctx, nRedo), 128, 4 * smemPerWarp, strm>>>(
+			    ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nRedo, (char *)(*db.scratch).p, (char *)db.dp_tx.p,
+			    db.dp_ntx.as<int>(), cnt, ctx->coop, smemPerWarp, dbgPtr);
+			ctx->ktime_end();
+#else
+			KLAUNCH_ON(strm, 4, k_dp_units, launch_grid(ctx, nRedo), 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nRedo,
+			           (char *)(*db.scratch).p, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, ctx->coop, smemPerWarp, dbgPtr);
+#endif
+			++launches;
+			CK(cudaGetLastError());
+			CK(cudaStreamSynchronize(strm)); // the scratch and the order list are reused by the next sub-chunk
+			k0 = k1;
+		}
+		return 0;
+	};
+	auto dp_finish = [&](DpPending &pd, cudaStream_t strm, DpBufs &db, int *cnt) -> int {
+		if (!pd.active) return 0;
+		pd.active = false;
+		const int nUnits = (int)pd.units.size();
+		int hOvf = 0;
+		CK(cudaMemcpyAsync(&hOvf, db.dp_ovf.p, sizeof(int), cudaMemcpyDeviceToHost, strm));
+		CK(cudaStreamSynchronize(strm));
+		lap("dp program kernel");
+		if (dpDbg && useV2) dp_print(pd.units, strm, "program");
+		if (hOvf > 0) {
+			std::vector<int> hn((size_t)nUnits);
+			CK(cudaMemcpy(hn.data(), db.dp_ntx.p, sizeof(int) * (size_t)nUnits, cudaMemcpyDeviceToHost));
+			std::vector<int> redo;
+			for (int u = 0; u < nUnits; ++u)
+				if (hn[(size_t)u] < 0) redo.push_back(u);
+			if (dpDbg) {
+				CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 8 * (size_t)(nUnits + 1), strm));
+			}
+			if (dp_walk_units(pd, redo, strm, db, cnt) != 0) return 1;
+			lap("dp walk kernel (overflowed units)");
+			if (dpDbg) dp_print(pd.units, strm, "walk");
+		}
+		if (!db.dp_merge_scr.ensure((size_t)pd.mAcc + 16) || !upload(ctx, db.list, pd.comps.data(), pd.comps.size(), strm) ||
+		    !upload(ctx, db.dp_scr_off, pd.mergeOff.data(), pd.mergeOff.size(), strm))
+			return ctx->fail("out of device memory (DP merge)");
+		CK(cudaMemsetAsync(cnt, 0, 32, strm));
+		KLAUNCH_ON(strm, 7, k_dp_merge, launch_grid(ctx, pd.nComp), 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.list.as<int>(), pd.nComp,
+		           db.dp_ntx.as<int>(), (const char *)db.dp_tx.p, (char *)db.dp_merge_scr.p, db.dp_scr_off.as<long long>(), cnt, ctx->coop);
+		++launches;
+		CK(cudaGetLastError());
+		return 0;
+	};
+	// issues the DP of `comps` chunk by chunk; all chunks but the last are finished here, the last one is left in `pd`
+	auto dp_launch = [&](const std::vector<int> &comps, cudaStream_t strm, DpBufs &db, int *cnt, DpPending &pd) -> int {
+		size_t i0 = 0;
+		while (i0 < comps.size()) {
+			if (pd.active) {
+				if (dp_finish(pd, strm, db, cnt) != 0) return 1;
+				CK(cudaStreamSynchronize(strm)); // the merge reads the buffers the next chunk overwrites
+			}
+			pd.units.clear();
+			pd.mergeOff.clear();
+			std::vector<long long> cost;
+			long long tAcc = 0, mAcc = 0;
+			size_t arenaBytes = 0;
+			size_t i1 = i0;
+			while (i1 < comps.size()) {
+				int c = comps[i1];
+				int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
+				int W = (n + 63) / 64;
+				long long cap = rowOff[(size_t)c + 1] - rowOff[(size_t)c];
+				// the reference visits the samples in descending number of constraints (qsort ascending,
+				// stable, walked from the back: Q11)
+				std::vector<int> ord((size_t)S);
+				for (int s = 0; s < S; ++s) ord[(size_t)s] = s;
+				std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+					return ctx->samples[(size_t)a].h_ncon[(size_t)c] < ctx->samples[(size_t)b].h_ncon[(size_t)c];
+				});
+				std::vector<DpUnit> mine;
+				long long tNeed = 0;
+				size_t aNeed = 0;
+				int downsampleCnt = -1;
+				for (int oi = S - 1; oi >= 0; --oi) {
+					int s = ord[(size_t)oi];
+					int C = ctx->samples[(size_t)s].h_ncon[(size_t)c], M = ctx->samples[(size_t)s].h_npair[(size_t)c];
+					DpUnit u;
+					u.comp = c;
+					u.sample = s;
+					u.iterBound = oi == S - 1 ? C : 100;
+					u.stride = 0;
+					if (ctx->prm.max_dp_constraint_size <= 0) {
+						bool down = (C > 1000 && (long long)C * 10 < M) || (downsampleCnt > 0 && C >= downsampleCnt) || n >= 1500;
+						if (down) { // TranscriptDecider.cpp:3214-3227
+							int stride = C > 0 ? M / C : 1;
+							if (downsampleCnt > 0) stride = C / downsampleCnt;
+							if (stride < 1) stride = 1;
+							u.stride = stride;
+							if (downsampleCnt <= 0) downsampleCnt = (C + stride - 1) / stride;
+						}
+					}
+					if (u.iterBound < 1) u.iterBound = 1;
+					u.scratch_off = 0;
+					u.tx_off = tAcc + tNeed;
+					tNeed += (long long)dp_txlist_layout(nullptr, nullptr, u.iterBound, W);
+					aNeed = std::max(aNeed, dp2_layout(nullptr, nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100), 0));
+					mine.push_back(u);
+				}
+				long long mNeed = (long long)dp_merge_layout(nullptr, nullptr, W, cap);
+				if (i1 > i0 && (size_t)(tAcc + tNeed + mAcc + mNeed) > ctx->mem_budget) break;
+				for (auto &u : mine) {
+					// algorithmic bytes of the DP kernel: the sample's constraint table read once, its transcript list written once
+					dpBytes += (long long)ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] * (8LL * W + 40) + (long long)u.iterBound * (8LL * W + 8);
+					pd.units.push_back(u);
+					cost.push_back((long long)u.iterBound * (ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] + 1));
+				}
+				tAcc += tNeed;
+				pd.mergeOff.push_back(mAcc);
+				mAcc += mNeed;
+				arenaBytes = std::max(arenaBytes, aNeed);
+				++i1;
+			}
+			const int nUnits = (int)pd.units.size();
+			pd.nComp = (int)(i1 - i0);
+			pd.comps.assign(comps.begin() + (long)i0, comps.begin() + (long)i1);
+			pd.mAcc = mAcc;
+			std::vector<int> order((size_t)nUnits);
+			for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
+			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+			// one arena per cooperative group of the grid; fewer groups when the arenas would not fit the budget
+			arenaBytes = (arenaBytes + 255) & ~(size_t)255;
+			const long long groupsPerBlock = 128 / ctx->coop;
+			long long blocks = (nUnits + groupsPerBlock - 1) / groupsPerBlock;
+			blocks = std::min<long long>(blocks, (long long)ctx->n_sm * PSC_DP2_MINBLOCKS);
+			{
+				long long fit = (long long)(ctx->mem_budget / (arenaBytes * (size_t)groupsPerBlock));
+				blocks = std::max<long long>(1, std::min(blocks, fit));
+			}
+			if (!db.dp_tx.ensure((size_t)tAcc + 16) || !db.dp_ntx.ensure(sizeof(int) * (size_t)(nUnits + 1)) || !db.dp_ovf.ensure(64) ||
+			    !db.dp_arena.ensure((size_t)blocks * (size_t)groupsPerBlock * arenaBytes + 16))
+				return ctx->fail("out of device memory (DP program arenas)");
+			CK(cudaMemsetAsync(db.dp_ntx.p, useV2 ? 0 : 0xff, sizeof(int) * (size_t)(nUnits + 1), strm));
+			CK(cudaMemsetAsync(db.dp_ovf.p, 0, 64, strm));
+			if (!upload(ctx, db.dp_units, pd.units.data(), pd.units.size(), strm) || !upload(ctx, db.dp_order, order.data(), order.size(), strm))
+				return ctx->fail("out of device memory");
+			lap("dp host prep");
+			CK(cudaMemsetAsync(cnt, 0, 32, strm));
+			long long *dbgPtr = nullptr;
+			if (dpDbg) {
+				if (!st.dp_dbg.ensure(sizeof(long long) * 8 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
+				CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 8 * (size_t)(nUnits + 1), strm));
+				dbgPtr = st.dp_dbg.as<long long>();
+			}
+			if (useV2) {
+				KLAUNCH_ON(strm, 10, k_dp2_units, (int)blocks, 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits,
+				           (char *)db.dp_arena.p, arenaBytes, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, db.dp_ovf.as<int>(), ctx->coop, dbgPtr);
+				++launches;
+				CK(cudaGetLastError());
+			} else {
+				int one = nUnits; // every unit goes to the walk engine
+				CK(cudaMemcpyAsync(db.dp_ovf.p, &one, sizeof(int), cudaMemcpyHostToDevice, strm));
+				CK(cudaStreamSynchronize(strm));
+			}
+			pd.active = true;
+			i0 = i1;
+		}
 		return 0;
 	};
 	// The DP kernel ends with a long tail: a handful of (component, sample) units run for most of its duration
@@ -659,18 +792,23 @@ int psc_solve(psc_ctx *ctx)
 	size_t pass1Tx = 0;
 	bool twoPasses = false;
 	if (!heavy.empty()) {
-		if (run_dp(heavy, ctx->stream, st.db[0], counter, false) != 0) return 1;
-		if (run_dp(rest, ctx->stream2, st.db[1], counter + 8, true) != 0) return 1;
+		DpPending pdH, pdR;
+		if (dp_launch(heavy, ctx->stream, st.db[0], counter, pdH) != 0) return 1;
+		if (dp_launch(rest, ctx->stream2, st.db[1], counter + 8, pdR) != 0) return 1;
+		if (dp_finish(pdR, ctx->stream2, st.db[1], counter + 8) != 0) return 1;
 		CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream2));
 		CK(cudaStreamSynchronize(ctx->stream2));
+		lap("dp merge (second stream)");
 		if (run_units(1, ctx->stream2, st.ub[1], counter + 8) != 0) return 1;
 		pass1Tx = st.r_comp.size();
 		twoPasses = true;
 		lap("second stream (rest of DP, other components)");
-		CK(cudaStreamSynchronize(ctx->stream));
+		if (dp_finish(pdH, ctx->stream, st.db[0], counter) != 0) return 1;
 		lap("heavy DP tail");
 	} else if (!dpList.empty()) {
-		if (run_dp(dpList, ctx->stream, st.db[1], counter, true) != 0) return 1;
+		DpPending pd;
+		if (dp_launch(dpList, ctx->stream, st.db[1], counter, pd) != 0) return 1;
+		if (dp_finish(pd, ctx->stream, st.db[1], counter) != 0) return 1;
 	}
 	CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));

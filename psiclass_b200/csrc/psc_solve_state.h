@@ -15,11 +15,11 @@ struct UnitBufs {
 
 // device buffers of one DP launch sequence (k_dp_units + k_dp_merge)
 struct DpBufs {
-	DevBuf list, dp_scr_off, dp_order, dp_tx, dp_ntx, dp_units;
+	DevBuf list, dp_scr_off, dp_order, dp_tx, dp_ntx, dp_units, dp_arena, dp_ovf, dp_merge_scr;
 	DevBuf *scratch = nullptr;
 	void release()
 	{
-		DevBuf *all[] = {&list, &dp_scr_off, &dp_order, &dp_tx, &dp_ntx, &dp_units};
+		DevBuf *all[] = {&list, &dp_scr_off, &dp_order, &dp_tx, &dp_ntx, &dp_units, &dp_arena, &dp_ovf, &dp_merge_scr};
 		for (DevBuf *b : all) b->release();
 	}
 };
