@@ -127,15 +127,18 @@ static bool constraint_less(const Constraint &a, const Constraint &b)
 }
 
 // Constraints::CoalesceSameConstraints (Constraints.cpp:74-150).  std::sort leaves the order of
-// equal vectors unspecified; a stable sort is used here (fp sums are exact for NH in {1,2,4}: Q9).
-static void coalesce(ConstraintSet &cs)
+// equal vectors unspecified, and the weights 10/NH of equal vectors are summed in that order (Q9:
+// inexact for NH = 3).  The same std::sort call on the same sequence with the same comparator makes
+// the same moves whatever the element type, so calling it here reproduces the reference's order as
+// long as both are built against the same libstdc++ (checked against oracle/_ref/ref_dump).
+static void coalesce(ConstraintSet &cs, std::vector<int> *newIdxOut = nullptr)
 {
 	int size = (int)cs.c.size();
 	for (int i = 0; i < size; ++i)
 		cs.c[i].info = i;
 	std::vector<int> newIdx((size_t)size, 0);
 	if (size > 0) {
-		std::stable_sort(cs.c.begin(), cs.c.end(), constraint_less);
+		std::sort(cs.c.begin(), cs.c.end(), constraint_less);
 		int k = 0;
 		newIdx[cs.c[0].info] = 0;
 		for (int i = 1; i < size; ++i) {
@@ -174,6 +177,7 @@ static void coalesce(ConstraintSet &cs)
 		}
 		cs.p.resize((size_t)k + 1);
 	}
+	if (newIdxOut) newIdxOut->swap(newIdx);
 }
 
 // Constraints::ComputeNormAbund (Constraints.cpp:152-238)
@@ -238,9 +242,10 @@ void build_constraints(const Component &comp, Reads &r, bool primaryAsUnique, Co
 {
 	const std::vector<Subexon> &se = comp.se;
 	int seCnt = (int)se.size();
-	out.c.clear();
+	std::vector<Constraint>().swap(out.c); // capacity restarts at 0 for every component (Constraints.cpp:247-254)
 	out.p.clear();
 	int tag = 0;
+	int coalesceThreshold = 16384;
 	// mate bookkeeping: entries keyed by matePos; cache = ids whose stored matePos == cachedMatePos.
 	std::multimap<int, std::pair<uint64_t, int>> pending;
 	std::map<uint64_t, int> cache;
@@ -340,6 +345,16 @@ void build_constraints(const Component &comp, Reads &r, bool primaryAsUnique, Co
 				nm.effectiveCount = 2;
 				out.p.push_back(nm);
 			}
+		}
+		// capacity-triggered partial coalescing (Constraints.cpp:378-390).  The reference tests this after every
+		// primary convertible alignment, pushed or not; right after a coalesce size > threshold cannot hold
+		// together with size == capacity, so testing after pushes only is equivalent.
+		if ((int)out.c.size() > coalesceThreshold && out.c.size() == out.c.capacity()) {
+			std::vector<int> newIdx;
+			coalesce(out, &newIdx);
+			for (auto &e : pending) e.second.second = newIdx[(size_t)e.second.second]; // MateReadIds::UpdateIdx
+			for (auto &e : cache) e.second = newIdx[(size_t)e.second];
+			if (out.c.size() >= out.c.capacity() / 2) coalesceThreshold *= 2;
 		}
 	}
 	coalesce(out);
@@ -1896,7 +1911,10 @@ void solve(int compIdx, Component &comp, std::vector<ConstraintSet> &cs, const P
 			ConstraintSet &src = cs[complexity[i].first];
 			int iterBound = (int)src.c.size();
 			if (i < sampleCnt - 1) iterBound = 100;
-			if (i < sampleCnt - 10 && all.size() > 1000) iterBound = 10;
+			if (i < sampleCnt - 10 && all.size() > 1000) {
+				iterBound = 10;
+				if (stats) ++stats->nIter10;
+			}
 			if (prm.maxDpConstraintSize > 0) {
 				// TruncateConstraintsCoverFrom (Constraints.hpp:400-434)
 				std::vector<Constraint> tcv = src.c;
@@ -1919,8 +1937,11 @@ void solve(int compIdx, Component &comp, std::vector<ConstraintSet> &cs, const P
 				for (size_t q = 0; q < src.c.size(); q += (size_t)stride)
 					tcv.push_back(src.c[q]);
 				if (downsampleCnt <= 0) downsampleCnt = (int)tcv.size();
-				if (iterBound <= 10)
+				if (stats) ++stats->nDownsampled;
+				if (iterBound <= 10) {
+					if (stats) ++stats->nSkipped;
 					continue;
+				}
 				D.pickByDP(iterBound, tcv, attr, sampleTx);
 			} else
 				D.pickByDP(iterBound, src.c, attr, sampleTx);

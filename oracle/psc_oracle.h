@@ -84,6 +84,10 @@ struct OutTranscript {
 struct SolveStats {
 	int atCnt = 0;
 	int useDP = 0;
+	// which branches of the DP sample loop (TranscriptDecider.cpp:3196-3244) the component took (test coverage evidence)
+	int nDownsampled = 0; // samples that went through DownsampleConstraintsFrom
+	int nIter10 = 0;      // samples that got iterBound = 10
+	int nSkipped = 0;     // down-sampled samples skipped because iterBound <= 10
 };
 
 // Constraints::BuildConstraints (Constraints.cpp:240-438) for one sample and one component;

@@ -9,6 +9,7 @@
 //   ComputeNormAbund               Constraints.cpp:152-238
 #pragma once
 #include "psc_internal.h"
+#include "std_sort_order.h"
 
 namespace pscdev {
 
@@ -191,6 +192,7 @@ PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, 
 	}
 	co.sync();
 	int C = 0;
+	bool has3 = false;
 	for (int b0 = 0; b0 < V; b0 += co.n) {
 		int p = b0 + co.lane;
 		bool head = false;
@@ -220,10 +222,60 @@ PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, 
 			int nh = mt.w & 0xff;
 			int *cnt = (int *)&s.con_nhcnt[lo + cid];
 			if (nh >= 1 && nh <= 4) atomic_add(&cnt[nh - 1], 1);
+			has3 = has3 || nh == 3;
 		}
 		C += popc32(m);
 	}
+	has3 = co.any(has3);
 	co.sync();
+	// ---- C2: a group with NH = 3 reads: the weight sums are inexact, so they are accumulated in the order the
+	// reference's std::sort leaves equal constraints in, including its capacity-triggered partial coalescing
+	// (Constraints.cpp:378-390; the vector starts empty per component, :247-254, so capacities are 1, 2, 4, ...).
+	// comp(a, b) of CompSortConstraints is cid[a] < cid[b] now that the rows are numbered in sorted order.
+	if (has3) {
+		if (co.lane == 0) {
+			int *P = idx, *tk = idx + R, *ek = s.pair_uniq_in + lo;
+			double *ew = s.con_weight + lo, *tw = (double *)(s.pair_key + lo);
+			int size = 0, cap = 0, thr = 16384;
+			auto coalesce = [&]() {
+				if (size <= 0) return;
+				for (int i = 0; i < size; ++i) P[i] = i;
+				std_sort_order(P, size, [&](int x, int y) { return ek[x] < ek[y]; });
+				int k = 0;
+				tk[0] = ek[P[0]];
+				tw[0] = ew[P[0]];
+				for (int i = 1; i < size; ++i) {
+					int x = P[i];
+					if (ek[x] == tk[k]) tw[k] += ew[x];
+					else {
+						++k;
+						tk[k] = ek[x];
+						tw[k] = ew[x];
+					}
+				}
+				size = k + 1;
+				for (int i = 0; i < size; ++i) {
+					ek[i] = tk[i];
+					ew[i] = tw[i];
+				}
+			};
+			for (int r = 0; r < R; ++r) {
+				int4 mt = meta[r];
+				if (mt.x < 0) continue;
+				if (size == cap) cap = cap ? 2 * cap : 1;
+				int nh = mt.w & 0xff;
+				ek[size] = s.cand_cid[lo + r];
+				ew[size] = (1.0 / (double)(nh > 0 ? nh : 1)) * 10; // Constraints.cpp:294-296 with Q1
+				++size;
+				if (size > thr && size == cap) {
+					coalesce();
+					if (size >= cap / 2) thr *= 2;
+				}
+			}
+			coalesce(); // ek[k] == k and ew[k] == con_weight[lo + k] from here on
+		}
+		co.sync();
+	}
 	// ---- D: mate pairs ----
 	int M = 0;
 	if (s.frag_stdev == 0) {
@@ -342,8 +394,9 @@ PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, 
 	const int8_t *lt = g.lt + base, *rt = g.rt + base;
 	for (int k = co.lane; k < C; k += co.n) {
 		int4 nhc = s.con_nhcnt[lo + k];
-		// sum of (1.0/NH)*10 over the merged reads; exact (order-free) for NH in {1,2,4}
-		double weight = ((nhc.x * 10.0 + nhc.y * 5.0) + nhc.w * 2.5) + nhc.z * ((1.0 / 3) * 10);
+		// sum of (1.0/NH)*10 over the merged reads; exact (order-free) for NH in {1,2,4}, see C2 for NH = 3
+		double weight = (nhc.x * 10.0 + nhc.y * 5.0) + nhc.w * 2.5;
+		if (has3) weight = s.con_weight[lo + k];
 		int first = s.con_first[lo + k], last = s.con_last[lo + k];
 		const uint64_t *b = obits + (long long)k * W;
 		int readLen = s.con_maxlen[lo + k];

@@ -18,7 +18,7 @@ class SynthCfg(C.Structure):
                 ("p_skip", C.c_double), ("p_alt", C.c_double), ("p_ir", C.c_double), ("p_noise", C.c_double),
                 ("p_overlap", C.c_double), ("p_paralog", C.c_double), ("name_style", C.c_int32),
                 ("stranded", C.c_int32), ("dense", C.c_int32), ("graph_noise", C.c_int32),
-                ("single_end", C.c_int32), ("threads", C.c_int32)]
+                ("single_end", C.c_int32), ("threads", C.c_int32), ("p_nh3", C.c_double), ("frag_sd", C.c_double)]
 
 
 class CheckOpts(C.Structure):
@@ -31,7 +31,8 @@ class CheckReport(C.Structure):
                 ("tables_checked", C.c_longlong), ("tables_bad", C.c_longlong), ("stats_bad", C.c_longlong),
                 ("tx_engine", C.c_longlong), ("tx_oracle", C.c_longlong), ("tx_bad", C.c_longlong),
                 ("val_exact", C.c_longlong), ("val_close", C.c_longlong), ("val_bad", C.c_longlong),
-                ("launches", C.c_longlong), ("constraints_ms", C.c_double), ("solve_ms", C.c_double)]
+                ("launches", C.c_longlong), ("constraints_ms", C.c_double), ("solve_ms", C.c_double),
+                ("n_downsampled", C.c_longlong), ("n_iter10", C.c_longlong), ("n_skipped", C.c_longlong)]
 
     def summary(self):
         return ("pass=%d comps=%d dp=%d tables %d/%d bad, stats bad %d, tx engine/oracle %d/%d bad %d, "

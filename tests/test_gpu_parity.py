@@ -23,6 +23,10 @@ CONFIGS = [
     # four words (still the register-resident DP walk) and five words (the generic in-memory walk)
     dict(seed=21, n_genes=3, n_samples=2, exon_mu=5.3, exon_sigma=0.1, exon_min=180, exon_max=200, iso_lambda=2.0, p_alt=0.3, mean_pairs=150.0),
     dict(seed=22, n_genes=2, n_samples=2, exon_mu=5.6, exon_sigma=0.1, exon_min=230, exon_max=260, iso_lambda=2.0, p_alt=0.3, mean_pairs=150.0),
+    # NH = 3: inexact weights 10/3, summed in std::sort's order of equal constraints (Q9), also in groups deep
+    # enough for the capacity-triggered partial coalescing (Constraints.cpp:378-390)
+    dict(seed=31, n_genes=200, n_samples=3, mean_pairs=300.0, p_nh3=0.2, iso_lambda=3.0, p_alt=0.3),
+    dict(seed=33, n_genes=3, n_samples=2, mean_pairs=60000.0, p_nh3=0.15, iso_lambda=3.0, p_alt=0.3),
 ]
 
 
@@ -116,24 +120,81 @@ def test_randomised_workload_shapes(seed, monkeypatch):
     assert rep.passed, "%s %s: %s" % (cfg, mode, rep.summary())
 
 
+def test_dense_component_unlimited_dp():
+    """BASELINE configs[3] in miniature: a dense component of 317 subexons (5 words), --maxDpConstraintSize -1
+    (constraints are not truncated, so DP keys grow long)."""
+    wl = testkit.Workload.synth(seed=1003, n_genes=1, n_samples=3, dense=1, exon_min=80, exon_max=100, mean_pairs=300.0, threads=8)
+    rep = wl.check(abi.LIB_PATH, max_dp=-1)
+    assert rep.passed, rep.summary()
+    assert rep.n_dp == 1
+
+
+@pytest.mark.parametrize("mean_pairs", [12.0, 40.0])
+def test_downsampling_branch_of_the_dp_sample_loop(mean_pairs):
+    """--maxDpConstraintSize -1 on a component of 1587 subexons and 13 samples: DownsampleConstraintsFrom
+    (n >= 1500, TranscriptDecider.cpp:3214-3227), iterBound = 10 after ten samples with > 1000 candidates
+    (:3203) and the skip of such down-sampled samples (:3228)."""
+    wl = testkit.Workload.synth(seed=1003, n_genes=1, n_samples=13, dense=1, exon_min=460, exon_max=470, mean_pairs=mean_pairs, threads=8)
+    rep = wl.check(abi.LIB_PATH, max_dp=-1)
+    assert rep.passed, rep.summary()
+    assert rep.n_downsampled == 13 and rep.n_iter10 >= 1 and rep.n_skipped >= 1
+
+
+def test_primary_paralog_stranded_many_samples():
+    """BASELINE configs[4] in miniature: paralog pairs (NH = 2, one primary + one secondary copy), --primaryParalog,
+    rf-stranded flags, 13 samples so that the iterBound = 10 rule fires on the heavy DP components."""
+    wl = testkit.Workload.synth(seed=1004, n_genes=16, n_samples=13, p_paralog=0.2, stranded=1, mean_pairs=1500.0, exon_mu=3.6,
+                                exon_sigma=0.3, iso_lambda=10.0, p_alt=0.5, p_ir=0.1, threads=8)
+    rep = wl.check(abi.LIB_PATH, primary_paralog=1)
+    assert rep.passed, rep.summary()
+    assert rep.n_iter10 >= 10 and rep.n_dp >= 10
+
+
 def test_flags_unlimited_dp_and_primary_paralog():
     wl = testkit.Workload.synth(seed=45, n_genes=25, n_samples=3, mean_pairs=150.0, exon_mu=2.0, iso_lambda=3.0, p_alt=0.3, threads=8)
     assert wl.check(abi.LIB_PATH, max_dp=-1).passed
     assert wl.check(abi.LIB_PATH, primary_paralog=1).passed
 
 
-@pytest.mark.parametrize("name", ["synth_small", "dp_small"])
-@pytest.mark.parametrize("gpus", [1])
+# fixture -> extra `classes` arguments it was generated with (tests/golden/make_golden.sh); `example` is the
+# reference's own example/ (BASELINE configs[0], SURVEY Appendix A)
+FIXTURES = {"synth_small": [], "dp_small": [], "nh3_small": [], "example": [], "dense_down": ["--maxDpConstraintSize", "-1"]}
+
+
+def n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+@pytest.mark.parametrize("gpus", [1, 2])
 def test_drop_in_classes_reproduces_reference_gtfs(name, gpus, tmp_path):
-    """The whole drop-in (`classes` binary -> C ABI -> CUDA) against GTFs the unmodified reference wrote."""
+    """The whole drop-in (`classes` binary -> C ABI -> CUDA) against GTFs the unmodified reference wrote;
+    gpus=2 shards the components over two devices (skipped on a one-GPU box)."""
+    if gpus > n_devices():
+        pytest.skip("needs %d CUDA devices" % gpus)
     d = stage_fixture(name, tmp_path)
     env = dict(os.environ, PSC_GPUS=str(gpus))
-    out = run([CLASSES, "--lb", "bamlist", "-s", "subexon_combined.out", "-o", "new", "-p", "4"], cwd=d, env=env)
+    out = run([CLASSES, "--lb", "bamlist", "-s", "subexon_combined.out", "-o", "new", "-p", "4"] + FIXTURES[name], cwd=d, env=env)
     n = len(open(os.path.join(d, "bamlist")).read().split())
     for s in range(n):
         assert gtf_body(os.path.join(d, "new_sample_%d.gtf" % s)) == gtf_body(os.path.join(d, "ref_sample_%d.gtf" % s))
     golden = [ln for ln in open(os.path.join(d, "ref_dump.txt")).read().splitlines() if "atCnt=" in ln]
     assert [ln for ln in out.splitlines() if "atCnt=" in ln] == golden
+    if name == "example":  # SURVEY Appendix A
+        body = gtf_body(os.path.join(d, "new_sample_0.gtf"))
+        assert 'FPKM "240454.413473"; TPM "1000000.000000"; cov "9.233449";' in body[0]
+        assert 'FPKM "283446.712018"; TPM "1000000.000000"; cov "7.142857";' in gtf_body(os.path.join(d, "new_sample_1.gtf"))[0]
+
+
+def test_bench_workload_shape_against_the_oracle():
+    """A tenth of the bench workload (BASELINE configs[1]: same generator, seed and shape, 6 000 gene models,
+    10 samples, ~13.5 M alignment records) compared with the oracle table by table and transcript by transcript;
+    the two-stream schedule is what runs at this size.  tools/gpu_parity_large.py does the same at 60 000."""
+    wl = testkit.Workload.synth(seed=1001, n_chr=24, n_genes=6000, n_samples=10, mean_pairs=60.0, threads=8)
+    rep = wl.check(abi.LIB_PATH, coop=32)
+    assert rep.passed, rep.summary()
+    assert rep.n_comp > 5000 and rep.tables_checked == rep.n_comp * 10 and rep.val_bad == 0 and rep.tx_bad == 0
 
 
 def test_properties_at_scale(tmp_path):

@@ -18,12 +18,44 @@ CLASSES_SHIM = os.path.join(ROOT, "tests", "shim", "_build", "classes_shim")
     dict(seed=44, n_genes=40, n_samples=5, p_paralog=0.15, stranded=1, name_style=2, p_noise=0.1, p_overlap=0.15),
     # ~146 subexons per component: three 64-bit words per bit vector, DP path, int32 path-count overflow (Q4)
     dict(seed=20, n_genes=4, n_samples=3, exon_mu=4.8, exon_sigma=0.1, exon_min=110, exon_max=120, iso_lambda=2.0, p_alt=0.3, mean_pairs=150.0),
+    # NH = 3: inexact weights, summed in std::sort's order of equal constraints (Q9)
+    dict(seed=31, n_genes=60, n_samples=3, mean_pairs=300.0, p_nh3=0.2, iso_lambda=3.0, p_alt=0.3),
+    # ... in groups of several 100 000 reads: the capacity-triggered partial coalescing (Constraints.cpp:378-390)
+    dict(seed=33, n_genes=3, n_samples=2, mean_pairs=60000.0, p_nh3=0.15, iso_lambda=3.0, p_alt=0.3),
 ])
 def test_kernel_logic_matches_oracle_on_cpu_shim(cfg):
     wl = testkit.Workload.synth(threads=4, **cfg)
     rep = wl.check(testkit.SHIM_PATH, coop=1)
     assert rep.passed, rep.summary()
     assert rep.tables_checked == wl.n_comp * wl.n_samples and rep.val_close == 0
+
+
+def test_dp_sample_loop_branches_on_cpu_shim():
+    """--maxDpConstraintSize -1 on a component of 1587 subexons and 13 samples: DownsampleConstraintsFrom
+    (n >= 1500), iterBound = 10 after ten samples with > 1000 candidates, and the skip of such samples
+    (TranscriptDecider.cpp:3196-3235)."""
+    wl = testkit.Workload.synth(seed=1003, n_genes=1, n_samples=13, dense=1, exon_min=460, exon_max=470, mean_pairs=12.0, threads=4)
+    rep = wl.check(testkit.SHIM_PATH, coop=1, max_dp=-1)
+    assert rep.passed, rep.summary()
+    assert rep.n_downsampled == 13 and rep.n_iter10 >= 1 and rep.n_skipped >= 1
+
+
+def test_primary_paralog_stranded_many_samples_on_cpu_shim():
+    """BASELINE configs[4] in miniature: paralog pairs (NH = 2 primary + secondary), --primaryParalog, rf-stranded
+    flags, 13 samples so that the iterBound = 10 rule fires on the heavy DP components."""
+    wl = testkit.Workload.synth(seed=1004, n_genes=5, n_samples=13, p_paralog=0.2, stranded=1, mean_pairs=1500.0, exon_mu=3.6,
+                                exon_sigma=0.3, iso_lambda=10.0, p_alt=0.5, p_ir=0.1, threads=4)
+    rep = wl.check(testkit.SHIM_PATH, coop=1, primary_paralog=1)
+    assert rep.passed, rep.summary()
+    assert rep.n_iter10 >= 1 and rep.n_dp >= 3
+
+
+def test_std_sort_order_restatement_equals_libstdcxx(tmp_path):
+    """psiclass_b200/csrc/std_sort_order.h makes the moves of libstdc++'s std::sort (needed for the NH = 3 sums)."""
+    exe = str(tmp_path / "std_sort_check")
+    run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "std_sort_check.cpp")])
+    out = run([exe, "6000"])
+    assert "mismatches 0" in out, out
 
 
 def test_two_pass_schedule_keeps_component_major_output(monkeypatch):
@@ -82,14 +114,17 @@ def test_bam_roundtrip_equals_direct_records(tmp_path):
         assert testkit.lib().tk_total_read_cnt(wl.h, s) == testkit.lib().tk_total_read_cnt(w2.h, s)
 
 
-@pytest.mark.parametrize("name", ["synth_small", "dp_small"])
+FIXTURES = {"synth_small": [], "dp_small": [], "nh3_small": [], "example": [], "dense_down": ["--maxDpConstraintSize", "-1"]}
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
 @pytest.mark.parametrize("shards", [1, 3])
 def test_front_end_reproduces_reference_gtfs(name, shards, tmp_path):
     """argv handling, single-pass BAM decode, component sharding, Q8 and the GTF writer: the drop-in
     `classes` (linked against the shim here) must print the reference's GTF bodies byte for byte."""
     d = stage_fixture(name, tmp_path)
     env = dict(os.environ, PSC_GPUS=str(shards))
-    out = run([CLASSES_SHIM, "--lb", "bamlist", "-s", "subexon_combined.out", "-o", "new", "-p", "3"], cwd=d, env=env)
+    out = run([CLASSES_SHIM, "--lb", "bamlist", "-s", "subexon_combined.out", "-o", "new", "-p", "3"] + FIXTURES[name], cwd=d, env=env)
     n = len(open(os.path.join(d, "bamlist")).read().split())
     for s in range(n):
         assert gtf_body(os.path.join(d, "new_sample_%d.gtf" % s)) == gtf_body(os.path.join(d, "ref_sample_%d.gtf" % s))

@@ -20,11 +20,18 @@ def atcnt_lines(text):
     return [ln for ln in text.splitlines() if "atCnt=" in ln]
 
 
-@pytest.mark.parametrize("name", ["synth_small", "dp_small"])
+# fixture -> extra `classes` arguments it was generated with (tests/golden/make_golden.sh)
+FIXTURES = {"synth_small": [], "dp_small": [], "nh3_small": [], "example": [],
+            "dense_down": ["--maxDpConstraintSize", "-1"]}
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
 def test_oracle_matches_golden(name, tmp_path):
     d = stage_fixture(name, tmp_path)
-    out = run([ORACLE, "-s", "subexon_combined.out", "--lb", "bamlist", "-o", "orc", "--dump"], cwd=d)
+    out = run([ORACLE, "-s", "subexon_combined.out", "--lb", "bamlist", "-o", "orc", "--dump"] + FIXTURES[name], cwd=d)
     golden = open(os.path.join(d, "ref_dump.txt")).read()
+    if name == "dense_down":  # the fixture keeps no constraint / pair rows (size); everything else is compared
+        out = "\n".join(ln for ln in out.splitlines() if not ln.startswith(("c ", "m ")))
     # library stats, component list + gene ids, every constraint / mate-pair table, totalReadCnt (Q8)
     assert dump_lines(out) == dump_lines(golden)
     # atCnt / seCnt / useDP / #constraints / #matePairs of every Solve
@@ -58,6 +65,8 @@ def test_example_known_answer(tmp_path):
     ["--genes", "60", "--samples", "3", "--seed", "31", "--name-style", "2", "--p-noise", "0.1", "--p-overlap", "0.15"],
     ["--genes", "30", "--samples", "4", "--seed", "32", "--pairs", "200", "--exon-mu", "2.2", "--iso-lambda", "4", "--p-alt", "0.3"],
     ["--genes", "40", "--samples", "2", "--seed", "33", "--single-end", "1"],
+    # NH = 3 reads in groups deep enough (> 32768 constraints) for the capacity-triggered partial coalescing
+    ["--genes", "3", "--samples", "2", "--seed", "33", "--pairs", "60000", "--p-nh3", "0.15", "--iso-lambda", "3", "--p-alt", "0.3"],
 ])
 def test_oracle_matches_live_reference(args, tmp_path):
     if not os.path.exists(REF_DUMP):

@@ -221,6 +221,8 @@ int run_check(const psc::Graph &g, std::vector<psc::SampleReads> &samples, const
 	rep.tx_engine = nt; rep.tx_oracle = (long long)otx.size(); rep.tx_bad = txBad;
 	rep.val_exact = valExact; rep.val_close = valClose; rep.val_bad = valBad;
 	rep.constraints_ms = tm.constraints_ms; rep.solve_ms = tm.solve_ms; rep.launches = tm.kernel_launches;
+	rep.n_downsampled = rep.n_iter10 = rep.n_skipped = 0;
+	for (auto &o : ostats) { rep.n_downsampled += o.nDownsampled; rep.n_iter10 += o.nIter10; rep.n_skipped += o.nSkipped; }
 	rep.pass = fail ? 0 : 1;
 	return fail ? 1 : 0;
 }

@@ -27,5 +27,6 @@ struct CheckReport {
 	int pass, n_comp, n_dp;
 	long long tables_checked, tables_bad, stats_bad, tx_engine, tx_oracle, tx_bad, val_exact, val_close, val_bad, launches;
 	double constraints_ms, solve_ms;
+	long long n_downsampled, n_iter10, n_skipped; // oracle-side branch counters (orc::SolveStats)
 };
 int run_check(const psc::Graph &g, std::vector<psc::SampleReads> &samples, const EngineApi &api, const CheckOpts &opt, CheckReport &rep);

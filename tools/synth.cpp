@@ -72,7 +72,7 @@ void make_genes(const Config &cfg, Workload &w)
 		g.strand = rng.uni() < cfg.p_minus ? -1 : 1;
 		int n;
 		if (cfg.dense)
-			n = rng.range(cfg.exon_min > 1 ? cfg.exon_min : 80, cfg.exon_max < 120 ? cfg.exon_max : 200);
+			n = rng.range(cfg.exon_min > 1 ? cfg.exon_min : 80, cfg.exon_max != 120 ? cfg.exon_max : 200);
 		else {
 			n = 1 + (int)std::floor(std::exp(cfg.exon_mu + cfg.exon_sigma * rng.normal()));
 			n = std::max(cfg.exon_min, std::min(cfg.exon_max, n));
@@ -448,6 +448,7 @@ void make_sample(const Workload &w, int sample, const std::string &bam_path, psc
 			double un = rng.uni();
 			if (un < cfg.p_nh4) nh = 4;
 			else if (un < cfg.p_nh4 + cfg.p_nh2) nh = 2;
+			else if (un < cfg.p_nh4 + cfg.p_nh2 + cfg.p_nh3) nh = 3;
 			if (noise == 6) nh = 6;
 			if (para) nh = 2;
 			bool leftFirst;

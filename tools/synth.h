@@ -27,6 +27,7 @@ struct Config {
 	int read_len = 100;
 	double frag_mean = 250, frag_sd = 30;
 	double p_nh2 = 0.04, p_nh4 = 0.02;
+	double p_nh3 = 0;          // NH=3 reads: 10/3 is inexact, so the order of the weight sum shows (Q9)
 	double p_noise = 0.04;     // clipped / intronic / indel / secondary / odd records
 	double p_minus = 0.5;
 	double p_overlap_gene = 0.05; // next gene placed antisense, overlapping the previous one

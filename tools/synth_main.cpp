@@ -40,6 +40,8 @@ int main(int argc, char **argv)
 		else if (o == "--dense") c.dense = nexti();
 		else if (o == "--graph-noise") c.graph_noise = nexti();
 		else if (o == "--single-end") c.single_end = nexti();
+		else if (o == "--p-nh3") c.p_nh3 = nextd();
+		else if (o == "--frag-sd") c.frag_sd = nextd();
 		else if (o == "--no-bam") writeBam = false;
 		else { fprintf(stderr, "synth: unknown option %s\n", argv[a]); return 1; }
 	}

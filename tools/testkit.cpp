@@ -29,6 +29,7 @@ struct tk_synth_cfg {
 	int32_t exon_min, exon_max;
 	double iso_lambda, p_skip, p_alt, p_ir, p_noise, p_overlap, p_paralog;
 	int32_t name_style, stranded, dense, graph_noise, single_end, threads;
+	double p_nh3, frag_sd;
 };
 
 static bool graph_from_text(tk_handle *h, const std::string &txt)
@@ -55,6 +56,7 @@ void tk_default_cfg(tk_synth_cfg *c)
 	c->p_alt = d.p_alt; c->p_ir = d.p_ir; c->p_noise = d.p_noise; c->p_overlap = d.p_overlap_gene; c->p_paralog = d.p_paralog;
 	c->name_style = d.name_style; c->stranded = d.stranded; c->dense = d.dense; c->graph_noise = d.graph_noise;
 	c->single_end = d.single_end; c->threads = 8;
+	c->p_nh3 = d.p_nh3; c->frag_sd = d.frag_sd;
 }
 
 tk_handle *tk_synth(const tk_synth_cfg *c)
@@ -67,6 +69,7 @@ tk_handle *tk_synth(const tk_synth_cfg *c)
 	d.p_alt = c->p_alt; d.p_ir = c->p_ir; d.p_noise = c->p_noise; d.p_overlap_gene = c->p_overlap; d.p_paralog = c->p_paralog;
 	d.name_style = c->name_style; d.stranded = c->stranded; d.dense = c->dense; d.graph_noise = c->graph_noise;
 	d.single_end = c->single_end;
+	d.p_nh3 = c->p_nh3; d.frag_sd = c->frag_sd;
 	synth::make_genes(d, h->w);
 	h->synthetic = true;
 	if (!graph_from_text(h, synth::subexon_text(h->w))) return h;
