@@ -13,9 +13,16 @@ only.  One "step" = one full pass of the hot path over the whole batch:
 
 With N > 1 (torchrun, one rank per GPU) every rank processes its own workload of the same size
 (weak scaling, no data-path collective); the time is the max over ranks.
+
+File legs (rank 0): the SAME workload written as BAM files + combined subexon file and run through the
+drop-in `psiclass_b200/bin/classes` (PSC_GPUS=N: ONE workload sharded by component over the N devices,
+strong scaling) -- BAM on disk -> GTF on disk, wall clock around the process -> `e2e_files`, with a sha256 of
+the GTF bodies.  `--impl reference` runs the unmodified reference `classes -p <cores>` on the same files
+(same generator, same seed, same size) and prints the same digest, so the two arms are like for like.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import shutil
@@ -105,44 +112,79 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def run_reference_cpu(cfg, steps, warmup, cores):
-    """Times the unmodified reference `classes` (oracle/_ref, built from /root/reference) on a bounded
-    sample of the workload, on all host cores (-p cores)."""
+def write_workload_files(cfg, cores, wl=None):
+    """The workload as files: <dir>/subexon_combined.out, s<i>.bam, bamlist.  Returns (dir, #components, bytes)."""
+    from psiclass_b200 import testkit
+    own = wl is None
+    if own:
+        wl = testkit.Workload.synth(threads=cores, **cfg)
+    d = tempfile.mkdtemp(prefix="psc_bench_")
+    wl.write_files(d)
+    ncomp = wl.n_comp
+    if own:
+        wl.close()
+    nbytes = 0
+    for f in os.listdir(d):  # warm the page cache
+        with open(os.path.join(d, f), "rb") as fh:
+            while True:
+                b = fh.read(1 << 24)
+                if not b:
+                    break
+                nbytes += len(b)
+    return d, ncomp, nbytes
+
+
+def gtf_digest(d, prefix, n_samples):
+    """sha256 over the GTF bodies ('#' header lines carry argv and paths) of all samples, in order."""
+    h = hashlib.sha256()
+    lines = 0
+    for s in range(n_samples):
+        with open(os.path.join(d, "%s_sample_%d.gtf" % (prefix, s)), "rb") as f:
+            for ln in f:
+                if not ln.startswith(b"#"):
+                    h.update(ln)
+                    lines += 1
+    return h.hexdigest(), lines
+
+
+def run_classes(binary, d, prefix, threads, gpus=None, extra_env=None):
+    """One `classes` process on the files in d; returns (seconds, perf dict or None)."""
+    env = dict(os.environ)
+    perf_path = None
+    if gpus is not None:
+        env["PSC_GPUS"] = str(gpus)
+        perf_path = os.path.join(d, prefix + "_perf.json")
+        env["PSC_PERF_JSON"] = perf_path
+    if extra_env:
+        env.update(extra_env)
+    cmd = [binary, "--lb", os.path.join(d, "bamlist"), "-s", os.path.join(d, "subexon_combined.out"),
+           "-o", os.path.join(d, prefix), "-p", str(threads)]
+    t0 = time.perf_counter()
+    subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True, env=env)
+    dt = time.perf_counter() - t0
+    perf = None
+    if perf_path and os.path.exists(perf_path):
+        try:
+            perf = json.load(open(perf_path))
+        except Exception:
+            perf = None
+    return dt, perf
+
+
+def reference_binary():
     from psiclass_b200 import testkit
     ref = os.path.join(testkit.REF_DIR, "classes")
-    kind = "reference"
-    if not os.path.exists(ref):
-        ref = os.path.join(testkit.REF_DIR, "psc_oracle")  # the CPU restatement
-        kind = "port"
-    if not os.path.exists(ref):
-        return None
-    wl = testkit.Workload.synth(threads=cores, **cfg)
-    d = tempfile.mkdtemp(prefix="psc_bench_")
-    try:
-        wl.write_files(d)
-        ncomp = wl.n_comp
-        # warm the page cache
-        for f in os.listdir(d):
-            with open(os.path.join(d, f), "rb") as fh:
-                while fh.read(1 << 24):
-                    pass
-        times = []
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            cmd = [ref, "--lb", os.path.join(d, "bamlist"), "-s", os.path.join(d, "subexon_combined.out"),
-                   "-o", os.path.join(d, "out"), "-p", str(cores if kind == "reference" else 1)]
-            subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
-            dt = time.perf_counter() - t0
-            if it >= warmup:
-                times.append(dt)
-        mean = sum(times) / len(times)
-        return {"value": ncomp / mean, "unit": UNIT, "cores": cores if kind == "reference" else 1, "kind": kind,
-                "sample": "%d components x %d samples (same generator and seed as the workload, %d gene models), "
-                          "BAM files on local disk, page cache warm, `classes -p %d`, %.2f s per pass"
-                          % (ncomp, cfg["n_samples"], cfg["n_genes"], cores, mean),
-                "seconds_per_pass": mean}
-    finally:
-        shutil.rmtree(d, ignore_errors=True)
+    if os.path.exists(ref):
+        return ref, "reference"
+    ref = os.path.join(testkit.REF_DIR, "psc_oracle")  # the CPU restatement (single-threaded)
+    if os.path.exists(ref):
+        return ref, "port"
+    return None, None
+
+
+def describe(cfg):
+    return "%d gene models on %d contigs, seed %d, %d samples, ~%d read pairs/component/sample" % (
+        cfg["n_genes"], cfg["n_chr"], cfg["seed"], cfg["n_samples"], int(cfg["mean_pairs"]))
 
 
 def main():
@@ -154,6 +196,8 @@ def main():
     ap.add_argument("--genes", type=int, default=None, help="override the number of gene models (debugging)")
     ap.add_argument("--coop", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the BAM -> GTF legs through the `classes` binary")
+    ap.add_argument("--ref-passes", type=int, default=2, help="timed passes of the reference arm (one pass is ~1-2 min)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -165,9 +209,7 @@ def main():
     if a.genes:
         cfg["n_genes"] = a.genes
         cpu_cfg["n_genes"] = min(a.genes, cpu_cfg["n_genes"])
-    config = {"workload": "synthetic 10-sample human-scale subexon graph, stage 3 only (BASELINE.json configs[1]): "
-                          "%d gene models on %d contigs, seed %d, %d samples, ~%d read pairs/component/sample"
-                          % (cfg["n_genes"], cfg["n_chr"], cfg["seed"], cfg["n_samples"], int(cfg["mean_pairs"])),
+    config = {"workload": "synthetic 10-sample human-scale subexon graph, stage 3 only (BASELINE.json configs[1]): " + describe(cfg),
               "l2": "inputs (alignment records + tables, several GB per GPU) are far larger than the 126 MB L2",
               "sharding": "components shard by rank with no collective; every rank assembles an identically generated "
                           "workload of this size (same seed), so the per-GPU work is exactly fixed as N grows"}
@@ -176,17 +218,38 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        warm = max(0, min(a.warmup, 1))
-        r = run_reference_cpu(cpu_cfg, a.steps, warm, cores)
-        if r is None:
+        ref, kind = reference_binary()
+        if ref is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built"}))
             return 0
-        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
-                "steps": a.steps, "warmup": warm, "ms_per_step": 1000.0 * r["seconds_per_pass"],
+        # The SAME workload as the CUDA arm (same generator, seed and size), as files.  One pass of the reference
+        # takes 1-2 minutes, so at most --ref-passes (2) timed passes run whatever --steps says, without a warm-up
+        # pass (the page cache is warmed by reading the files once).
+        passes = max(1, min(a.steps, a.ref_passes))
+        threads = cores if kind == "reference" else 1
+        d, ncomp, nbytes = write_workload_files(cfg, cores)
+        try:
+            times = []
+            for _ in range(passes):
+                dt, _ = run_classes(ref, d, "ref", threads)
+                times.append(dt)
+            digest, glines = gtf_digest(d, "ref", cfg["n_samples"])
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+        mean = sum(times) / len(times)
+        value = ncomp / mean
+        sample = ("the whole workload (%s): %d components, %.2f GB of BAM + subexon file on local disk, page cache warm, "
+                  "`classes -p %d` (BAM decode + stage 3 + GTF), %d timed passes of %.1f s, no warm-up pass"
+                  % (describe(cfg), ncomp, nbytes / 1e9, threads, passes, mean))
+        config["reference_passes"] = passes
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+                "steps": passes, "warmup": 0, "ms_per_step": 1000.0 * mean,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+u64",
                 "data": "synthetic", "config": config,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "e2e_files": {"value": value, "unit": UNIT, "seconds": mean, "components": ncomp, "bam_bytes": nbytes,
+                              "gtf_sha256": digest, "gtf_lines": glines},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return 0
@@ -202,6 +265,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # host-side wait while rank 0 runs the file legs
 
     # Same seed on every rank: the step time of this path is set by the single heaviest component of the
     # workload, which varies by +-50 % between seeds; identical replicas keep the per-GPU work fixed,
@@ -324,9 +388,16 @@ def main():
         launches_per_step = max(1, kcnt[dom] // max(1, a.steps))
         alg = kbytes[dom] / launches_per_step
         achieved = (alg / 1e9) / (per_launch_ms / 1e3) if per_launch_ms > 0 and alg > 0 else 0.0
-        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one `ncu --set full` capture of the
-        # default workload (profiles/r1_ncu_summary.md): the launch over the heavy DP components, 37.8 + 169.8 MB
-        traffic = 207.6e6 if (names[dom] == "dp_units" and not a.genes) else None
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: read from the JSON that
+        # tools/gpu/ncu_traffic.py wrote from an `ncu --set full` capture of this workload (profiles/), else null
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get("k_" + names[dom])
+            if ent and not a.genes:
+                traffic = float(ent["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": total_components * a.steps / wall_max, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * wall_max / a.steps,
@@ -344,17 +415,57 @@ def main():
             "components_per_rank": ncomp, "transcripts_per_rank": int(ntx),
             "reads_per_rank": int(sum(r.n_reads for r in reads)),
         }
-        if not a.no_cpu_baseline and world >= 1:
+        eng.close()
+        ours = os.path.join(ROOT, "psiclass_b200", "bin", "classes")
+        ref, kind = reference_binary()
+        if not a.no_cpu_baseline and world == 1 and ref is not None:
+            # the reference's CPU path on the box's host cores, on a bounded sample of the same workload (same generator
+            # and seed, 1/40 of the gene models); the drop-in runs on the same files and the GTFs are compared
             try:
-                r = run_reference_cpu(cpu_cfg, 1, 0, cores)
-                if r:
-                    line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                d, nc_s, nb_s = write_workload_files(cpu_cfg, cores)
+                try:
+                    threads = cores if kind == "reference" else 1
+                    t_ref, _ = run_classes(ref, d, "ref", threads)
+                    t_new, _ = run_classes(ours, d, "new", cores, gpus=1)
+                    same = gtf_digest(d, "ref", cpu_cfg["n_samples"]) == gtf_digest(d, "new", cpu_cfg["n_samples"])
+                finally:
+                    shutil.rmtree(d, ignore_errors=True)
+                line["cpu_baseline"] = {
+                    "value": nc_s / t_ref, "unit": UNIT, "cores": threads, "kind": kind,
+                    "sample": "%d components (%s): BAM files on local disk, page cache warm, `classes -p %d` (BAM decode + "
+                              "stage 3 + GTF), one pass of %.2f s; the whole workload is timed by `--impl reference`"
+                              % (nc_s, describe(cpu_cfg), threads, t_ref),
+                    "drop_in_same_files": {"seconds": t_new, "components_per_s": nc_s / t_new, "gtf_identical": bool(same)}}
             except Exception as e:  # the baseline is reported, never required
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "sample": "failed: %s" % e}
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": kind, "sample": "failed: %s" % e}
+        if not a.no_files:
+            # BAM on disk -> GTF on disk through the drop-in binary: ONE workload of the full size, sharded by
+            # component over the N devices (PSC_GPUS=N), no collective, final gather + global sort on the host
+            try:
+                d, nc_f, nb_f = write_workload_files(cfg, cores, wl)
+                try:
+                    t_new, perf = run_classes(ours, d, "new", cores, gpus=world)
+                    digest, glines = gtf_digest(d, "new", cfg["n_samples"])
+                finally:
+                    shutil.rmtree(d, ignore_errors=True)
+                ef = {"value": nc_f / t_new, "unit": UNIT, "seconds": t_new, "components": nc_f, "bam_bytes": nb_f,
+                      "n_gpus": world, "scaling": "strong", "host_threads": cores, "gtf_sha256": digest, "gtf_lines": glines}
+                if perf:
+                    sh = perf.get("shards", [])
+                    ef["phases_s"] = {k: perf.get(k) for k in ("decode_s", "graph_s", "device_s", "gtf_s", "total_s")}
+                    ef["decode_MBps"] = perf.get("decode_MBps")
+                    if sh:
+                        pipe = max(x["upload_s"] + x["constraints_s"] + x["solve_s"] + x["download_s"] for x in sh)
+                        ef["device_pipeline"] = {
+                            "seconds": pipe, "components_per_s": nc_f / pipe if pipe > 0 else None,
+                            "what": "max over the shards of upload + constraints + solve + download (one workload, sharded)",
+                            "shards": sh}
+                line["e2e_files"] = ef
+            except Exception as e:
+                line["e2e_files"] = {"value": None, "unit": UNIT, "error": str(e)}
         print(json.dumps(line))
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
     return 0
 

@@ -8,6 +8,7 @@
 #include <getopt.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -57,7 +58,14 @@ struct Shard {
 	std::vector<psc::OutTx> out;
 	std::vector<int32_t> at_cnt, use_dp, ncon0, npair0;
 	std::string err;
+	double upload_s = 0, constraints_s = 0, solve_s = 0, download_s = 0; // PSC_PERF_JSON
+	long long n_reads = 0;
 };
+
+static double now_s()
+{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static void run_shard(int device, const psc::Graph &g, const std::vector<psc::SampleReads> &samples, const psc_params &prm,
                       Shard &sh)
@@ -111,6 +119,7 @@ static void run_shard(int device, const psc::Graph &g, const std::vector<psc::Sa
 	pg.prev_off = sh.prev_off.data();
 	pg.prev_idx = g.prev_idx.data() + pe0;
 	E(psc_set_graph(ctx, &pg));
+	double t0 = now_s();
 	// reads of the shard: [first read the first component examines, last read the last component examines)
 	sh.chr_off.resize((size_t)S);
 	for (int s = 0; s < S; ++s) {
@@ -137,9 +146,16 @@ static void run_shard(int device, const psc::Graph &g, const std::vector<psc::Sa
 		r.read_len = sr.read_len;
 		r.frag_stdev = sr.frag_stdev;
 		E(psc_set_reads(ctx, s, &r));
+		sh.n_reads += r.n_reads;
 	}
+	double t1 = now_s();
 	E(psc_build_constraints(ctx));
+	double t2 = now_s();
 	E(psc_solve(ctx));
+	double t3 = now_s();
+	sh.upload_s = t1 - t0;
+	sh.constraints_s = t2 - t1;
+	sh.solve_s = t3 - t2;
 	std::vector<int32_t> nC((size_t)S * nc), nM((size_t)S * nc);
 	E(psc_constraint_counts(ctx, nC.data(), nM.data()));
 	sh.ncon0.assign(nC.begin(), nC.begin() + nc);
@@ -175,6 +191,7 @@ static void run_shard(int device, const psc::Graph &g, const std::vector<psc::Sa
 		o.tpm = 0;
 		for (int64_t e = eo[(size_t)k]; e < eo[(size_t)k + 1]; ++e) o.exons.push_back({es[(size_t)e], ee[(size_t)e]});
 	}
+	sh.download_s = now_s() - t3;
 	psc_destroy(ctx);
 #undef E
 }
@@ -232,6 +249,7 @@ int main(int argc, char *argv[])
 	}
 	int S = (int)bamPaths.size();
 	if (numThreads < 1) numThreads = 1;
+	const double tStart = now_s();
 	// ---- one decode pass per BAM (library statistics + alignment records), samples in parallel ----
 	std::vector<psc::SampleReads> samples((size_t)S);
 	std::vector<std::string> errs((size_t)S);
@@ -251,6 +269,7 @@ int main(int argc, char *argv[])
 			fprintf(stderr, "%s\n", errs[(size_t)s].c_str());
 			exit(1);
 		}
+	const double tDecoded = now_s();
 	psc::Graph g;
 	std::string err;
 	if (!psc::load_subexon_graph(subexonPath, samples[0].chr_names, classifierThreshold, g, err)) {
@@ -270,7 +289,8 @@ int main(int argc, char *argv[])
 	prm.frag_stdev = samples[0].frag_stdev;
 	prm.mate_paired = samples[0].mate_paired;
 
-	// ---- shard the components over the devices, balanced by read count ----
+	const double tGraph = now_s();
+	// ---- shard the components over the devices, balanced by an estimate of the device work ----
 	int nGpu = 1;
 	if (const char *e = getenv("PSC_GPUS")) nGpu = std::max(1, atoi(e));
 	nGpu = std::min(nGpu, std::max(1, g.n_comp));
@@ -301,7 +321,10 @@ int main(int argc, char *argv[])
 		for (int c2 = 0; c2 < g.n_comp; ++c2) {
 			long long r = 16;
 			for (int s = 0; s < S; ++s) r += last_read(s, c2) - first_read(s, c2);
-			cum[(size_t)c2 + 1] = cum[(size_t)c2] + r;
+			// constraint building is linear in the reads; candidate search and set cover grow with the number of
+			// subexons as well (the DP components, n >~ 20, carry most of the solve time)
+			long long n = g.comp_off[(size_t)c2 + 1] - g.comp_off[(size_t)c2];
+			cum[(size_t)c2 + 1] = cum[(size_t)c2] + r * (8 + n) / 8;
 		}
 		int c0 = 0;
 		for (int d = 0; d < nGpu; ++d) {
@@ -330,6 +353,7 @@ int main(int argc, char *argv[])
 			printf("%s\n", sh.err.c_str());
 			exit(1);
 		}
+	const double tDevice = now_s();
 	// ---- log (classes.cpp:299-302, TranscriptDecider.cpp:3111) and output ----
 	std::vector<psc::OutTx> queue;
 	for (auto &sh : shards) {
@@ -354,6 +378,29 @@ int main(int argc, char *argv[])
 	if (!psc::write_gtfs(queue, totalReadCnt, g.chr_names, prefix, argc, argv, bamPaths, err)) {
 		printf("%s\n", err.c_str());
 		exit(1);
+	}
+	if (const char *pj = getenv("PSC_PERF_JSON")) { // wall-clock of the phases, for bench.py (path of the file to write)
+		if (FILE *fp = fopen(pj, "w")) {
+			long long bamBytes = 0, nReads = 0;
+			for (auto &b : bamPaths)
+				if (FILE *f = fopen(b.c_str(), "rb")) {
+					fseek(f, 0, SEEK_END);
+					bamBytes += ftell(f);
+					fclose(f);
+				}
+			for (auto &sr : samples) nReads += sr.n_reads();
+			const double tEnd = now_s();
+			fprintf(fp, "{\"components\": %d, \"samples\": %d, \"gpus\": %d, \"host_threads\": %d, \"reads\": %lld, \"bam_bytes\": %lld, "
+			            "\"decode_s\": %.4f, \"decode_MBps\": %.1f, \"graph_s\": %.4f, \"device_s\": %.4f, \"gtf_s\": %.4f, \"total_s\": %.4f, \"shards\": [",
+			        g.n_comp, S, nGpu, numThreads, nReads, bamBytes, tDecoded - tStart, bamBytes / 1e6 / std::max(1e-9, tDecoded - tStart),
+			        tGraph - tDecoded, tDevice - tGraph, tEnd - tDevice, tEnd - tStart);
+			for (size_t d = 0; d < shards.size(); ++d)
+				fprintf(fp, "%s{\"components\": %d, \"reads\": %lld, \"upload_s\": %.4f, \"constraints_s\": %.4f, \"solve_s\": %.4f, \"download_s\": %.4f}",
+				        d ? ", " : "", shards[d].c1 - shards[d].c0, shards[d].n_reads, shards[d].upload_s, shards[d].constraints_s,
+				        shards[d].solve_s, shards[d].download_s);
+			fprintf(fp, "]}\n");
+			fclose(fp);
+		}
 	}
 	return 0;
 }

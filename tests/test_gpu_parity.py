@@ -129,7 +129,7 @@ def test_dense_component_unlimited_dp():
     assert rep.n_dp == 1
 
 
-@pytest.mark.parametrize("mean_pairs", [12.0, 40.0])
+@pytest.mark.parametrize("mean_pairs", [12.0, 25.0])
 def test_downsampling_branch_of_the_dp_sample_loop(mean_pairs):
     """--maxDpConstraintSize -1 on a component of 1587 subexons and 13 samples: DownsampleConstraintsFrom
     (n >= 1500, TranscriptDecider.cpp:3214-3227), iterBound = 10 after ten samples with > 1000 candidates
