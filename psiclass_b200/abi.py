@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpsc.so")
+LIB_PATH = os.environ.get("PSC_LIBPSC") or os.path.join(HERE, "libpsc.so")  # PSC_LIBPSC: build variants (tools/gpu)
 
 i32p = C.POINTER(C.c_int32)
 i64p = C.POINTER(C.c_int64)

@@ -998,10 +998,12 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 	co.sync();
 }
 
-// The same unit on the static-program engine (k_dp2.cuh).  `arena` is the calling group's private working set of
-// arenaBytes; a unit whose key / frame / list tables outgrow it reports *n_tx_out = -1 and is redone by the walk engine.
+// The same unit on the static-program engine (k_dp2.cuh).  `arena` is the calling group's private global working set
+// of arenaBytes, `hot` its slice of shared memory (or nullptr).  The unit first runs with its hot tables in shared
+// memory; if they outgrow the slice it starts over with everything in the arena; a unit whose key / frame / list
+// tables outgrow that too reports *n_tx_out = -1 and is redone by the walk engine.
 PSC_DEVN void dp2_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv, const DpUnit &u, char *arena, size_t arenaBytes,
-                            char *txBase, int *n_tx_out, long long *dbg)
+                            char *hot, size_t hotBytes, char *txBase, int *n_tx_out, long long *dbg)
 {
 	DpState st;
 	st.nStates = st.nLevels = st.nIters = st.nFrames = st.nRoots = st.cycRoot = st.cycAssign = 0;
@@ -1013,34 +1015,41 @@ PSC_DEVN void dp2_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &s
 	TableView t = table_view(sv.samples[u.sample], u.comp);
 	int Ccap = t.C > 100 ? t.C : 100;
 	Dp2 z;
-	size_t used = dp2_layout(&st.d, &z, arena, v.n, E, Ccap, arenaBytes);
-	if (used > arenaBytes || z.maxKeys < 8) { // does not even hold the fixed part
-		if (co.lane == 0) *n_tx_out = -1;
+	int nt = -1;
+	int inShared = 0;
+	// shared memory is tried only when the slice holds the tables of a typical unit of this size (~1.4 n keys on the
+	// bench workload): an attempt that overflows is thrown away
+	const bool trySmem = hot && dp2_hot_fixed(v.n, v.W) + (size_t)(3 * v.n / 2 + 8) * dp2_hot_per_key(v.W, DP2_FR_PER_KEY_SMEM) <= hotBytes;
+	for (int attempt = trySmem ? 0 : 1; attempt < 2; ++attempt) {
+		char *h = attempt == 0 ? hot : nullptr;
+		size_t used = dp2_layout(&st.d, &z, arena, arenaBytes, h, hotBytes, v.n, E, Ccap);
+		if (used > arenaBytes || z.maxKeys < 8 || (h && z.hotBytesUsed > hotBytes)) continue; // does not even hold the fixed part
+		inShared = h != nullptr;
+		for (int k = co.lane; k < v.n + 1; k += co.n) z.key1[k] = -1;
+		for (int k = co.lane; k < z.hashCap; k += co.n) z.khash[k] = -1;
+		DpTxList out;
+		dp_txlist_layout(&out, txBase + u.tx_off, u.iterBound, v.W);
+		st.d.txb = out.b;
+		st.d.txf = out.f;
+		st.d.txl = out.l;
+		st.d.txCap = u.iterBound;
+		st.cs = sv.can_start + v.base;
+		st.ce = sv.can_end + v.base;
+		st.W = v.W;
+		st.epoch = 0;
+		st.prof = dbg != nullptr;
+		st.err = sv.error_flag;
+		st.z = &z;
+		st.forAbundance = false;
+		st.minAbundance = 0;
+		st.timeStamp = 0;
+		dp_load_constraints(st, t, u.stride, sv.prm.maxDpConstraintSize);
 		co.sync();
-		return;
+		nt = dp_pick<DpEngineProgram>(st, u.iterBound);
+		co.sync();
+		if (!z.overflow) break;
+		nt = -1;
 	}
-	for (int k = co.lane; k < v.n + 1; k += co.n) z.key1[k] = -1;
-	for (int k = co.lane; k < z.hashCap; k += co.n) z.khash[k] = -1;
-	DpTxList out;
-	dp_txlist_layout(&out, txBase + u.tx_off, u.iterBound, v.W);
-	st.d.txb = out.b;
-	st.d.txf = out.f;
-	st.d.txl = out.l;
-	st.d.txCap = u.iterBound;
-	st.cs = sv.can_start + v.base;
-	st.ce = sv.can_end + v.base;
-	st.W = v.W;
-	st.epoch = 0;
-	st.prof = dbg != nullptr;
-	st.err = sv.error_flag;
-	st.z = &z;
-	st.forAbundance = false;
-	st.minAbundance = 0;
-	st.timeStamp = 0;
-	dp_load_constraints(st, t, u.stride, sv.prm.maxDpConstraintSize);
-	co.sync();
-	int nt = dp_pick<DpEngineProgram>(st, u.iterBound);
-	if (z.overflow) nt = -1;
 	if (co.lane == 0) *n_tx_out = nt;
 	if (dbg && co.lane == 0) {
 		dbg[0] = clock64() - t0;
@@ -1050,7 +1059,7 @@ PSC_DEVN void dp2_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &s
 		dbg[4] = z.nKeys;
 		dbg[5] = z.nFrames;
 		dbg[6] = z.nList;
-		dbg[7] = z.overflow ? -1 : z.maxKeys;
+		dbg[7] = nt < 0 ? -1 : (inShared ? -2 - (long long)z.maxKeys : z.maxKeys);
 	}
 	co.sync();
 }

@@ -66,7 +66,7 @@ struct Dp2 {
 	int *list;
 	int nList, maxList;
 	// activation stack of the interpreter
-	int *aKey, *aS, *aFi, *aLast, *aStrand;
+	int *aKey, *aS, *aFi, *aEnd, *aLast, *aStrand;
 	double *aCover, *aBeta;
 	uint64_t *aBits;
 	// walk stack of the compiler: index 0 is the key's last subexon
@@ -75,25 +75,46 @@ struct Dp2 {
 	uint64_t *tmp; // [W]
 	int depthCap;
 	int overflow;
+	size_t hotBytesUsed;
 };
 
-// bytes per key of the variable part: key record + 2 bit rows + 2 hash slots, 6 frames (+ bit row), 64 list entries
-__host__ __device__ inline size_t dp2_bytes_per_key(int W)
+// The working set has two parts.  HOT: what the interpreter touches on every step (key records with their memo,
+// key / memo / frame bit rows, frame records, the activation stack) -- it lives in the calling group's slice of
+// shared memory when it fits there, else in the group's global arena.  COLD: the constraint table handed to the DP,
+// the compatibility lists, the compiler's walk stack and the per-threshold result cache -- always global.
+#define DP2_FR_PER_KEY_SMEM 3
+#define DP2_FR_PER_KEY_GLOBAL 6
+#define DP2_LIST_PER_KEY 64
+__host__ __device__ inline size_t dp2_hot_fixed(int n, int W)
 {
-	return sizeof(Dp2Key) + 16 * (size_t)W + 16 + 6 * (sizeof(Dp2Frame) + 8 * (size_t)W) + 64 * sizeof(int);
+	size_t d = (size_t)n + 4;
+	// 6 int arrays, 2 double arrays, 1 bit-row array (each 16-byte aligned), key1, tmp
+	return 6 * ((4 * d + 15) & ~(size_t)15) + 2 * ((8 * d + 15) & ~(size_t)15) + ((8 * d * W + 15) & ~(size_t)15) +
+	       ((4 * ((size_t)n + 1) + 15) & ~(size_t)15) + ((8 * (size_t)W + 15) & ~(size_t)15) + 64;
+}
+__host__ __device__ inline size_t dp2_hot_per_key(int W, int frPerKey)
+{
+	return sizeof(Dp2Key) + 16 * (size_t)W + 16 + (size_t)frPerKey * (sizeof(Dp2Frame) + 8 * (size_t)W);
 }
 __host__ __device__ inline int dp2_wanted_keys(int n)
 {
 	long long k = 8LL * n + 128;
 	return (int)(k > 65536 ? 65536 : k);
 }
-
-// Carves one unit's working set out of `base`.  The fixed part depends on (n, E, Cmax); whatever is left of
-// arenaBytes goes to the key / frame / list tables.  With base == nullptr and arenaBytes == 0 returns the bytes
-// a unit needs for dp2_wanted_keys(n) keys.
-__host__ __device__ inline size_t dp2_layout(DpScratch *od, Dp2 *oz, char *base, int n, int E, int Cmax, size_t arenaBytes)
+// shared memory a unit would like: room for 2n + 32 keys (the heaviest units of the bench workload use ~1.4 n)
+__host__ __device__ inline size_t dp2_smem_wanted(int n)
 {
-	Carver cv(base);
+	int W = (n + 63) >> 6;
+	return dp2_hot_fixed(n, W) + (size_t)(2 * n + 32) * dp2_hot_per_key(W, DP2_FR_PER_KEY_SMEM) + 256;
+}
+
+// Carves one unit's working set.  cold/coldBytes: the group's global arena; hot/hotBytes: its shared-memory slice or
+// nullptr (then the hot part follows the cold part in the arena).  With cold == nullptr and coldBytes == 0 returns the
+// arena bytes a unit needs for dp2_wanted_keys(n) keys with everything in global memory.
+__host__ __device__ inline size_t dp2_layout(DpScratch *od, Dp2 *oz, char *cold, size_t coldBytes, char *hot, size_t hotBytes, int n,
+                                             int E, int Cmax)
+{
+	Carver cv(cold);
 	int W = (n + 63) >> 6;
 	DpScratch s;
 	s.ent = nullptr; s.eepoch = nullptr; s.ebits = nullptr; s.f2Base = 0; s.hashBase = 0; s.hashMax = 0;
@@ -120,45 +141,62 @@ __host__ __device__ inline size_t dp2_layout(DpScratch *od, Dp2 *oz, char *base,
 	s.covered = cv.take<int>((size_t)Cmax + 1);
 	Dp2 z;
 	z.depthCap = n + 4;
-	z.aKey = cv.take<int>((size_t)z.depthCap);
-	z.aS = cv.take<int>((size_t)z.depthCap);
-	z.aFi = cv.take<int>((size_t)z.depthCap);
-	z.aLast = cv.take<int>((size_t)z.depthCap);
-	z.aStrand = cv.take<int>((size_t)z.depthCap);
-	z.aCover = cv.take<double>((size_t)z.depthCap);
-	z.aBeta = cv.take<double>((size_t)z.depthCap);
-	z.aBits = cv.take<uint64_t>((size_t)z.depthCap * W);
 	z.wNode = cv.take<int>((size_t)z.depthCap);
 	z.wStrand = cv.take<int>((size_t)z.depthCap);
 	z.wEi = cv.take<int>((size_t)z.depthCap);
 	z.wExt = cv.take<int>((size_t)z.depthCap);
 	z.wUncov = cv.take<int>((size_t)z.depthCap);
 	z.wBits = cv.take<uint64_t>((size_t)z.depthCap * W);
-	z.tmp = cv.take<uint64_t>((size_t)W);
-	z.key1 = cv.take<int>((size_t)n + 1);
-	size_t fixed = (cv.off + 15) & ~(size_t)15;
-	long long K = dp2_wanted_keys(n);
-	if (arenaBytes > 0) {
-		K = arenaBytes > fixed + 64 ? (long long)((arenaBytes - fixed - 64) / dp2_bytes_per_key(W)) : 0;
+	const size_t coldFixed = (cv.off + 15) & ~(size_t)15;
+	const size_t hotFixed = dp2_hot_fixed(n, W);
+	const bool split = hot != nullptr;
+	const int frPerKey = split ? DP2_FR_PER_KEY_SMEM : DP2_FR_PER_KEY_GLOBAL;
+	long long K = dp2_wanted_keys(n), L;
+	if (coldBytes > 0) {
+		if (split) {
+			K = hotBytes > hotFixed + 64 ? (long long)((hotBytes - hotFixed - 64) / dp2_hot_per_key(W, frPerKey)) : 0;
+			L = coldBytes > coldFixed + 64 ? (long long)((coldBytes - coldFixed - 64) / sizeof(int)) : 0;
+			if (K > dp2_wanted_keys(n)) K = dp2_wanted_keys(n);
+		} else {
+			size_t perKey = dp2_hot_per_key(W, frPerKey) + DP2_LIST_PER_KEY * sizeof(int);
+			K = coldBytes > coldFixed + hotFixed + 64 ? (long long)((coldBytes - coldFixed - hotFixed - 64) / perKey) : 0;
+			L = DP2_LIST_PER_KEY * K;
+		}
 		if (K > 1 << 20) K = 1 << 20;
-	}
+	} else
+		L = DP2_LIST_PER_KEY * K;
+	if (L > (long long)DP2_LIST_PER_KEY * K) L = (long long)DP2_LIST_PER_KEY * K;
 	z.maxKeys = (int)K;
-	z.maxFrames = (int)(6 * K);
-	z.maxList = (int)(64 * K);
+	z.maxFrames = (int)(frPerKey * K);
+	z.maxList = (int)L;
 	z.hashCap = 4;
 	while (z.hashCap < 2 * K) z.hashCap <<= 1; // < 4K slots
-	z.keys = cv.take<Dp2Key>((size_t)z.maxKeys);
-	z.kbits = cv.take<uint64_t>((size_t)z.maxKeys * W);
-	z.mbits = cv.take<uint64_t>((size_t)z.maxKeys * W);
-	z.khash = cv.take<int>((size_t)z.hashCap);
-	z.frames = cv.take<Dp2Frame>((size_t)z.maxFrames);
-	z.fbits = cv.take<uint64_t>((size_t)z.maxFrames * W);
 	z.list = cv.take<int>((size_t)z.maxList);
+	Carver hv(split ? hot : cold);
+	if (!split) hv.off = (cv.off + 15) & ~(size_t)15;
+	z.aKey = hv.take<int>((size_t)z.depthCap);
+	z.aS = hv.take<int>((size_t)z.depthCap);
+	z.aFi = hv.take<int>((size_t)z.depthCap);
+	z.aEnd = hv.take<int>((size_t)z.depthCap);
+	z.aLast = hv.take<int>((size_t)z.depthCap);
+	z.aStrand = hv.take<int>((size_t)z.depthCap);
+	z.aCover = hv.take<double>((size_t)z.depthCap);
+	z.aBeta = hv.take<double>((size_t)z.depthCap);
+	z.aBits = hv.take<uint64_t>((size_t)z.depthCap * W);
+	z.tmp = hv.take<uint64_t>((size_t)W);
+	z.key1 = hv.take<int>((size_t)n + 1);
+	z.keys = hv.take<Dp2Key>((size_t)z.maxKeys);
+	z.kbits = hv.take<uint64_t>((size_t)z.maxKeys * W);
+	z.mbits = hv.take<uint64_t>((size_t)z.maxKeys * W);
+	z.khash = hv.take<int>((size_t)z.hashCap);
+	z.frames = hv.take<Dp2Frame>((size_t)z.maxFrames);
+	z.fbits = hv.take<uint64_t>((size_t)z.maxFrames * W);
+	z.hotBytesUsed = split ? hv.off : 0;
 	z.nKeys = z.nFrames = z.nList = 0;
 	z.overflow = 0;
 	if (od) *od = s;
 	if (oz) *oz = z;
-	return (cv.off + 15) & ~(size_t)15;
+	return split ? ((cv.off + 15) & ~(size_t)15) : ((hv.off + 15) & ~(size_t)15);
 }
 
 PSC_DEV uint32_t dp2_hash_bits(const uint64_t *b, int W)
@@ -642,6 +680,206 @@ PSC_DEVN int dp2_solve_root(DpState &stRef, int start)
 	return ret;
 }
 
+// The same interpreter for the common case (cover counting, forAbundance == false), NW = words per bit row known at
+// compile time: every table base pointer, the threshold and the current activation (best cover / beta / path bits
+// included) are registers, the three modes are straight-line code joined by gotos, and the cover scans reduce to a
+// comparison and an addition.  Results are identical to dp2_solve_root's by construction (same order, same rules).
+template <int NW> PSC_DEVN int dp3_solve_root(DpState &stRef, int start)
+{
+	Dp2 &z = *stRef.z;
+	if (z.key1[start] < 0) {
+		for (int w = 0; w < NW; ++w) z.tmp[w] = 0;
+		bt_set(z.tmp, start);
+		if (dp2_key(stRef, z.tmp, start, start, 1, 0) < 0) return -1;
+	}
+	Dp2Key *const keys = z.keys;
+	const Dp2Frame *const frames = z.frames;
+	const uint64_t *const kbits = z.kbits, *const fbits = z.fbits;
+	uint64_t *const mbits = z.mbits, *const aBits = z.aBits;
+	int *const aKey = z.aKey, *const aFi = z.aFi, *const aEnd = z.aEnd, *const aLast = z.aLast, *const aStrand = z.aStrand;
+	double *const aCover = z.aCover, *const aBeta = z.aBeta;
+	const int depthCap = z.depthCap;
+	const double tau = stRef.minAbundance;
+	const bool tauPos = tau > 0;
+	const int ts = stRef.timeStamp, iter = stRef.iter;
+	int depth = -1, nStates = 0, nFrames = 0;
+	int t_key = 0, t_fi = 0, t_end = 0;
+	double o_cover = -1, o_beta = 1e300;
+	int o_plast = 0, o_pstrand = 0;
+	uint64_t ob[NW];
+	int rk = z.key1[start], rs = 0, ret = -1;
+call : {
+	Dp2Key *k = keys + rk;
+	{
+		// dp2_hit with forAbundance == false
+		const double kc = k->cover;
+		bool hit = false;
+		if (kc != -1 && k->mstrand == rs) {
+			const double kmin = k->minAb;
+			hit = k->ts == ts || (kmin < tau && kc == -2) ||
+			      (k->mode == 0 && k->iter == iter && kc >= 0 && kmin > 0 && tau > kmin && k->beta > tau);
+		}
+		if (hit) {
+			ret = rk;
+			if (depth < 0) goto done;
+			goto eval;
+		}
+	}
+	if (k->prog[rs + 1] < 0) {
+		dp2_compile(stRef, rk, rs + 1);
+		if (z.overflow) return -1;
+	}
+	++nStates;
+	if (depth >= 0) {
+		aKey[depth] = t_key;
+		aFi[depth] = t_fi;
+		aEnd[depth] = t_end;
+		aCover[depth] = o_cover;
+		aBeta[depth] = o_beta;
+		aLast[depth] = o_plast;
+		aStrand[depth] = o_pstrand;
+#pragma unroll
+		for (int w = 0; w < NW; ++w) aBits[depth * NW + w] = ob[w];
+	}
+	++depth;
+	if (depth >= depthCap) {
+		z.overflow = 1;
+		return -1;
+	}
+	t_key = rk;
+	t_fi = k->prog[rs + 1];
+	t_end = t_fi + k->nfr[rs + 1];
+	// pdp starts as the key itself (.cpp:722-760)
+	o_cover = -1;
+	o_beta = 1e300;
+	o_plast = k->last;
+	o_pstrand = rs;
+#pragma unroll
+	for (int w = 0; w < NW; ++w) ob[w] = kbits[rk * NW + w];
+	if (k->ownOff >= 0) {
+		o_cover = 0;
+		if (k->ownCnt > 0) {
+			const double mn = k->ownMinNorm;
+			if (mn <= tau) o_cover = -2;
+			else {
+				o_beta = mn;
+				o_cover = k->ownPos;
+			}
+		}
+	}
+}
+next:
+	if (t_fi == t_end) {
+		// the activation is finished: SetDpContent (.cpp:824-856)
+		Dp2Key *k = keys + t_key;
+#pragma unroll
+		for (int w = 0; w < NW; ++w) mbits[t_key * NW + w] = ob[w];
+		k->mlast = o_plast;
+		k->mstrand = o_pstrand;
+		k->cover = o_cover;
+		k->beta = o_beta;
+		k->iter = iter;
+		k->mode = 0;
+		k->minAb = tau;
+		k->ts = ts;
+		ret = t_key;
+		--depth;
+		if (depth < 0) goto done;
+		t_key = aKey[depth];
+		t_fi = aFi[depth];
+		t_end = aEnd[depth];
+		o_cover = aCover[depth];
+		o_beta = aBeta[depth];
+		o_plast = aLast[depth];
+		o_pstrand = aStrand[depth];
+#pragma unroll
+		for (int w = 0; w < NW; ++w) ob[w] = aBits[depth * NW + w];
+		goto eval;
+	}
+	{
+		const int nested = frames[t_fi].nested;
+		if (nested >= 0) {
+			rk = nested;
+			rs = (frames[t_fi].flags & 3) - 1;
+			goto call;
+		}
+		ret = -1;
+	}
+eval : {
+	// ---- evaluate frame t_fi given the sub-solution `ret` (.cpp:425-614) ----
+	++nFrames;
+	const Dp2Frame *fr = frames + t_fi;
+	const int flags = fr->flags;
+	const int fstrand = (flags & 3) - 1;
+	const bool uncov = (flags & DP2_F_UNCOV) != 0;
+	double vcover = -1;
+	if (ret >= 0) {
+		const Dp2Key *vk = keys + ret;
+		vcover = vk->cover;
+		if (vcover >= 0) {
+			double cover = vcover, cbeta = vk->beta;
+			bool belowMin = tauPos && uncov;
+			if (fr->sCnt > 0) {
+				const double mn = fr->minNormS;
+				if (mn <= tau) {
+					belowMin = true;
+					cover = -2;
+				} else {
+					if (mn < cbeta) cbeta = mn;
+					cover += fr->sPos;
+				}
+			}
+			const bool first = belowMin && o_cover == -1;
+			if (first || (!first && cover > o_cover)) {
+				o_cover = first ? -2 : cover;
+				o_beta = cbeta;
+				o_plast = vk->mlast;
+				o_pstrand = fstrand;
+#pragma unroll
+				for (int w = 0; w < NW; ++w) ob[w] = kbits[t_key * NW + w] | mbits[ret * NW + w];
+			}
+		} else if (vcover == -2 && o_cover == -1) {
+			o_cover = -2;
+			o_plast = vk->mlast;
+			o_pstrand = fstrand;
+#pragma unroll
+			for (int w = 0; w < NW; ++w) ob[w] = kbits[t_key * NW + w] | mbits[ret * NW + w];
+		}
+	}
+	// the path may also stop at this subexon (.cpp:524-614)
+	if ((flags & DP2_F_TERM) && vcover < 0) {
+		bool below = tauPos && uncov;
+		double cover = 0, cbeta = 1e300;
+		if (fr->tCnt > 0) {
+			const double mn = fr->minNormT;
+			if (mn <= tau) {
+				below = true;
+				cover = -2;
+			} else {
+				cbeta = mn;
+				cover = fr->tPos;
+			}
+		}
+		const bool first = below && o_cover == -1;
+		if (first || (!first && cover > o_cover)) {
+			o_cover = first ? -2 : cover;
+			o_beta = cbeta;
+			o_plast = fr->tag;
+			o_pstrand = fstrand;
+#pragma unroll
+			for (int w = 0; w < NW; ++w) ob[w] = fbits[t_fi * NW + w];
+		}
+	}
+	++t_fi;
+	goto next;
+}
+done:
+	stRef.nStates += nStates;
+	stRef.nFrames += nFrames;
+	++stRef.nRoots;
+	return ret;
+}
+
 // an abundance ran dry: recount the positive entries of every list
 PSC_DEV void dp2_refresh(DpState &st)
 {
@@ -680,7 +918,13 @@ struct DpEngineProgram {
 		o.bits = st.z->mbits;
 		o.first = o.last = i;
 		if (st.z->overflow) return o;
-		int r = dp2_solve_root(st, i);
+		int r;
+		if (st.forAbundance) r = dp2_solve_root(st, i);
+		else if (st.W == 1) r = dp3_solve_root<1>(st, i);
+		else if (st.W == 2) r = dp3_solve_root<2>(st, i);
+		else if (st.W == 3) r = dp3_solve_root<3>(st, i);
+		else if (st.W == 4) r = dp3_solve_root<4>(st, i);
+		else r = dp2_solve_root(st, i);
 		if (r < 0) return o;
 		const Dp2Key *k = st.z->keys + r;
 		o.cover = k->cover;

@@ -3,15 +3,21 @@
 #include "../../include/psc.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <type_traits>
 #include <vector>
+
+#ifndef PSC_CPU_SHIM
+#include <cuda.h> // types only: the driver entry points are looked up at run time (cudaGetDriverEntryPoint)
+#endif
 
 #include "psc_internal.h"
 #include "k_constraints.cuh"
@@ -128,6 +134,16 @@ struct psc_ctx {
 	int device = 0;
 	cudaStream_t stream = 0;
 	cudaStream_t stream2 = 0; // per-unit kernels of the enumerated components, running under the DP kernel's tail
+	// psc_solve's streams.  When the driver offers green contexts the SMs are split into a small partition for the
+	// few critical (component, sample) units whose single-warp latency chains set the step time (they then run one
+	// warp per SM sub-partition, undisturbed) and the rest for everything else: sMain / sSecond live in the big
+	// partition, sCrit in the small one.  Otherwise these are ordinary streams (sMain == stream, sSecond == stream2).
+	cudaStream_t sMain = 0, sSecond = 0, sCrit = 0;
+	cudaEvent_t evCritGo = 0, evCritDone = 0;
+	int critSms = 0; // SMs of the critical partition, 0: no partitioning
+#ifndef PSC_CPU_SHIM
+	CUgreenCtx gctxCrit = nullptr, gctxRest = nullptr;
+#endif
 	cudaEvent_t ev0 = 0, ev1 = 0;
 	std::string err;
 	psc_params prm;
@@ -183,8 +199,12 @@ struct psc_ctx {
 		evIds.clear();
 		evUsed = 0;
 	}
+	// psc_solve drives its two streams from two host threads: launches (with their timing events) and the error
+	// string are serialised
+	std::mutex launchMu, errMu;
 	int fail(const std::string &m)
 	{
+		std::lock_guard<std::mutex> lk(errMu);
 		err = m;
 		return 1;
 	}
@@ -199,6 +219,7 @@ struct psc_ctx {
 
 #define KLAUNCH_ON(strm, id, kernel, grid, block, ...)             \
 	do {                                                            \
+		std::lock_guard<std::mutex> lk_(ctx->launchMu);              \
 		ctx->ktime_begin(id, strm);                                  \
 		PSC_LAUNCH(kernel, grid, block, strm, __VA_ARGS__);          \
 		ctx->ktime_end();                                            \
@@ -243,6 +264,64 @@ int psc_create(psc_ctx **out, int device)
 	}
 	memset(&ctx->timing, 0, sizeof(ctx->timing));
 	memset(&ctx->prm, 0, sizeof(ctx->prm));
+	cudaEventCreateWithFlags(&ctx->evCritGo, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->evCritDone, cudaEventDisableTiming);
+	ctx->sMain = ctx->stream;
+	ctx->sSecond = ctx->stream2;
+#ifndef PSC_CPU_SHIM
+	// SM partitioning (PSC_CRIT_SMS=<n> SMs for the critical partition, default 16; 0 disables)
+	{
+		int want = 16;
+		if (const char *e = getenv("PSC_CRIT_SMS")) want = atoi(e);
+		if (want > 0 && ctx->n_sm >= 4 * want) {
+			typedef CUresult (*fnDevGet)(CUdevice *, int);
+			typedef CUresult (*fnGetRes)(CUdevice, CUdevResource *, CUdevResourceType);
+			typedef CUresult (*fnSplit)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+			typedef CUresult (*fnDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+			typedef CUresult (*fnCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+			typedef CUresult (*fnStream)(CUstream *, CUgreenCtx, unsigned int, int);
+			auto sym = [](const char *name) -> void * {
+				void *f = nullptr;
+				cudaDriverEntryPointQueryResult q;
+				if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+				return f;
+			};
+			fnDevGet devGet = (fnDevGet)sym("cuDeviceGet");
+			fnGetRes getRes = (fnGetRes)sym("cuDeviceGetDevResource");
+			fnSplit split = (fnSplit)sym("cuDevSmResourceSplitByCount");
+			fnDesc mkDesc = (fnDesc)sym("cuDevResourceGenerateDesc");
+			fnCreate mkCtx = (fnCreate)sym("cuGreenCtxCreate");
+			fnStream mkStream = (fnStream)sym("cuGreenCtxStreamCreate");
+			bool ok = devGet && getRes && split && mkDesc && mkCtx && mkStream;
+			CUdevice dev = 0;
+			CUdevResource all, crit, rest;
+			unsigned int groups = 1;
+			CUdevResourceDesc dCrit = nullptr, dRest = nullptr;
+			CUstream a = nullptr, b = nullptr, c = nullptr;
+			ok = ok && devGet(&dev, device) == CUDA_SUCCESS && getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+			     split(&crit, &groups, &all, &rest, 0, (unsigned int)want) == CUDA_SUCCESS && groups == 1 && rest.sm.smCount > 0 &&
+			     mkDesc(&dCrit, &crit, 1) == CUDA_SUCCESS && mkDesc(&dRest, &rest, 1) == CUDA_SUCCESS &&
+			     mkCtx(&ctx->gctxCrit, dCrit, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+			     mkCtx(&ctx->gctxRest, dRest, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+			     mkStream(&a, ctx->gctxRest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS &&
+			     mkStream(&b, ctx->gctxRest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS &&
+			     mkStream(&c, ctx->gctxCrit, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+			if (ok) {
+				ctx->sMain = (cudaStream_t)a;
+				ctx->sSecond = (cudaStream_t)b;
+				ctx->sCrit = (cudaStream_t)c;
+				ctx->critSms = (int)crit.sm.smCount;
+				if (getenv("PSC_DEBUG_HOST"))
+					fprintf(stderr, "[host] SM partitions: %u critical + %u\n", crit.sm.smCount, rest.sm.smCount);
+			} else
+				cudaGetLastError();
+		}
+	}
+#endif
+	if (!ctx->sCrit && cudaStreamCreate(&ctx->sCrit) != cudaSuccess) {
+		delete ctx;
+		return 5;
+	}
 	*out = ctx;
 	return 0;
 }
@@ -263,6 +342,22 @@ void psc_destroy(psc_ctx *ctx)
 	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
+	cudaEventDestroy(ctx->evCritGo);
+	cudaEventDestroy(ctx->evCritDone);
+	cudaStreamDestroy(ctx->sCrit);
+	if (ctx->sMain != ctx->stream) cudaStreamDestroy(ctx->sMain);
+	if (ctx->sSecond != ctx->stream2) cudaStreamDestroy(ctx->sSecond);
+#ifndef PSC_CPU_SHIM
+	{
+		typedef CUresult (*fnDestroy)(CUgreenCtx);
+		void *f = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if ((ctx->gctxCrit || ctx->gctxRest) && cudaGetDriverEntryPoint("cuGreenCtxDestroy", &f, cudaEnableDefault, &q) == cudaSuccess && f) {
+			if (ctx->gctxCrit) ((fnDestroy)f)(ctx->gctxCrit);
+			if (ctx->gctxRest) ((fnDestroy)f)(ctx->gctxRest);
+		}
+	}
+#endif
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->stream2);
 	delete ctx;

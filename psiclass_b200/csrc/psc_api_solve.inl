@@ -70,25 +70,32 @@ __global__ void __launch_bounds__(128, PSC_DP_MINBLOCKS) k_dp_units(GraphDev g, 
 	}
 }
 
-// The static-program DP engine (k_dp2.cuh): every cooperative group of the grid owns one arena of arenaBytes and
-// pulls (component, sample) units, heaviest first.  Units that outgrow their arena report n_tx = -1 and are counted
-// in *overflow; the host redoes them with k_dp_units.
+// The static-program DP engine (k_dp2.cuh): every cooperative group of the grid owns one global arena of arenaBytes
+// and a slice of hotBytes of the block's dynamic shared memory, and pulls (component, sample) units, heaviest first.
+// Units that outgrow their arena report n_tx = -1 and are counted in *overflow; the host redoes them with k_dp_units.
+// The block size is 128 (four units side by side) for the bulk of the units and 32 for the heavy launch, whose single
+// group gets most of an SM's shared memory.
 #ifndef PSC_DP2_MINBLOCKS
 #define PSC_DP2_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(128, PSC_DP2_MINBLOCKS) k_dp2_units(GraphDev g, SolveDev sv, const DpUnit *units, const int *order, int nUnits,
-                                                                    char *arenas, size_t arenaBytes, char *txArena, int *n_tx, int *counter,
-                                                                    int *overflow, int width, long long *dbg)
+                                                                    char *arenas, size_t arenaBytes, size_t hotBytes, char *txArena, int *n_tx,
+                                                                    int *counter, int *overflow, int width, long long *dbg)
 {
 	Coop co = make_coop(width);
 	char *arena = arenas + (size_t)coop_id(width) * arenaBytes;
+	char *hot = nullptr;
+#ifndef PSC_CPU_SHIM
+	extern __shared__ __align__(16) unsigned char dp2_smem[];
+	if (width == 32 && hotBytes > 0) hot = (char *)dp2_smem + (size_t)(threadIdx.x >> 5) * hotBytes;
+#endif
 	for (;;) {
 		int u = 0;
 		if (co.lane == 0) u = atomic_add(counter, 1);
 		u = co.bcast(u, 0);
 		if (u >= nUnits) break;
 		int ui = order[u];
-		dp2_unit_pick(co, g, sv, units[ui], arena, arenaBytes, txArena, n_tx + ui, dbg ? dbg + 8 * (long long)ui : nullptr);
+		dp2_unit_pick(co, g, sv, units[ui], arena, arenaBytes, hot, hotBytes, txArena, n_tx + ui, dbg ? dbg + 8 * (long long)ui : nullptr);
 		if (co.lane == 0 && n_tx[ui] < 0) atomic_add(overflow, 1);
 		co.sync();
 	}
@@ -112,7 +119,10 @@ __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const
 
 // phase: 1 pick round 1, 2 pick round 2 + filtration, 3 rescue.  list[0 .. nList): the chunk-local units of this pass,
 // heaviest first
-__global__ void __launch_bounds__(128, 4) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *list, int nList,
+#ifndef PSC_UNITS_MINBLOCKS
+#define PSC_UNITS_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, PSC_UNITS_MINBLOCKS) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *list, int nList,
                                                int *counter, int width, long long *dbg)
 {
 	Coop co = make_coop(width);
@@ -230,19 +240,23 @@ int psc_solve(psc_ctx *ctx)
 	if (!ctx->constraints_built) return ctx->fail("psc_build_constraints must run before psc_solve");
 	SolveState &st = ctx->solve;
 	const int S = ctx->prm.n_samples, nc = ctx->gd.n_comp, ns = ctx->gd.n_se;
-	long long launches = 0;
+	std::atomic<long long> launches{0};
 	// PSC_DEBUG_HOST=1: wall-clock of the host-side sections (stderr)
 	const bool hostDbg = getenv("PSC_DEBUG_HOST") != nullptr;
-	auto hostT0 = std::chrono::steady_clock::now();
+	const auto solveT0 = std::chrono::steady_clock::now();
+	const std::thread::id mainThread = std::this_thread::get_id();
+	std::chrono::steady_clock::time_point hostT0[2] = {solveT0, solveT0}; // [1]: the helper thread of the second stream
 	auto lap = [&](const char *what) {
 		if (!hostDbg) return;
+		const int who = std::this_thread::get_id() == mainThread ? 0 : 1;
 		auto t = std::chrono::steady_clock::now();
-		fprintf(stderr, "[host] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - hostT0).count());
-		hostT0 = t;
+		fprintf(stderr, "[host%s] %-28s %8.2f ms  (at %8.2f)\n", who ? " 2" : "", what, std::chrono::duration<double, std::milli>(t - hostT0[who]).count(),
+		        std::chrono::duration<double, std::milli>(t - solveT0).count());
+		hostT0[who] = t;
 	};
-	CK(cudaEventRecord(ctx->ev0, ctx->stream));
-	st.r_comp.clear(); st.r_sample.clear(); st.r_chr.clear(); st.r_gene.clear(); st.r_strand.clear();
-	st.r_exon_off.assign(1, 0); st.r_exon_start.clear(); st.r_exon_end.clear(); st.r_fpkm.clear(); st.r_cov.clear();
+	CK(cudaStreamSynchronize(ctx->stream)); // uploads and the constraint build ran on the context's primary stream
+	CK(cudaEventRecord(ctx->ev0, ctx->sMain));
+	st.reset();
 	st.h_at_cnt.assign((size_t)nc, 0); st.h_use_dp.assign((size_t)nc, 0); st.h_n_cand.assign((size_t)nc, 0);
 	if (nc == 0) {
 		ctx->solved = true;
@@ -273,7 +287,7 @@ int psc_solve(psc_ctx *ctx)
 	          st.error_flag.ensure(64) && st.fscratch.ensure(sizeof(int) * ((size_t)ns + 1)) &&
 	          upload(ctx, st.fs_off, fsOff.data(), (size_t)nc + 1);
 	if (!ok) return ctx->fail("out of device memory (solve state)");
-	CK(cudaMemsetAsync(st.error_flag.p, 0, 64, ctx->stream));
+	CK(cudaMemsetAsync(st.error_flag.p, 0, 64, ctx->sMain));
 	sv.can_start = st.can_start.as<uint8_t>();
 	sv.can_end = st.can_end.as<uint8_t>();
 	sv.edge_support = st.edge_support.as<int>();
@@ -287,13 +301,13 @@ int psc_solve(psc_ctx *ctx)
 
 	// the edge_support array is indexed with the global next-edge index: next_off is global already
 	// ---- P1: prologue ----
-	CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
-	KLAUNCH(2, k_prologue, launch_grid(ctx, nc), 128, ctx->gd, sv, st.fscratch.as<int>(), st.fs_off.as<int>(), counter, ctx->coop);
+	CK(cudaMemsetAsync(counter, 0, 64, ctx->sMain));
+	KLAUNCH_ON(ctx->sMain, 2, k_prologue, launch_grid(ctx, nc), 128, ctx->gd, sv, st.fscratch.as<int>(), st.fs_off.as<int>(), counter, ctx->coop);
 	++launches;
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(st.h_at_cnt.data(), sv.at_cnt, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaMemcpyAsync(st.h_use_dp.data(), sv.use_dp, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpyAsync(st.h_at_cnt.data(), sv.at_cnt, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->sMain));
+	CK(cudaMemcpyAsync(st.h_use_dp.data(), sv.use_dp, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->sMain));
+	CK(cudaStreamSynchronize(ctx->sMain));
 
 	lap("prologue");
 	// ---- candidate capacities ----
@@ -341,25 +355,25 @@ int psc_solve(psc_ctx *ctx)
 	if (!enumList.empty()) {
 		if (!upload(ctx, st.list, enumList.data(), enumList.size()) || !st.stk.ensure(sizeof(int) * 3 * ((size_t)ns + 1)))
 			return ctx->fail("out of device memory");
-		CK(cudaMemsetAsync(counter, 0, 64, ctx->stream));
+		CK(cudaMemsetAsync(counter, 0, 64, ctx->sMain));
 		// the enumeration is sequential per component: always one thread per unit
 		int saved = ctx->coop;
 		ctx->coop = 1;
 		int grid = launch_grid(ctx, (long long)enumList.size());
 		ctx->coop = saved;
-		KLAUNCH(3, k_enumerate, grid, 128, ctx->gd, sv, st.list.as<int>(), (int)enumList.size(), st.stk.as<int>(), st.fs_off.as<int>(),
+		KLAUNCH_ON(ctx->sMain, 3, k_enumerate, grid, 128, ctx->gd, sv, st.list.as<int>(), (int)enumList.size(), st.stk.as<int>(), st.fs_off.as<int>(),
 		        counter, 1);
 		++launches;
 		CK(cudaGetLastError());
-		CK(cudaStreamSynchronize(ctx->stream)); // enumList staging buffer is reused below
+		CK(cudaStreamSynchronize(ctx->sMain)); // enumList staging buffer is reused below
 	}
-	CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->sMain));
+	CK(cudaStreamSynchronize(ctx->sMain));
 	// ---- P3..P6 per chunk of components, as a pass over all components (pass 0), over all but the heavy DP
 	// components (1) or over the heavy DP components (2).  Pass 1 runs on the second stream with its own buffers
 	// while the heavy DP units are still busy on the main one. ----
 	std::vector<char> group((size_t)nc, 0); // 2: heavy DP component
-	auto run_units = [&](int pass, cudaStream_t strm, UnitBufs &ub, int *cnt) -> int {
+	auto run_units = [&](int pass, cudaStream_t strm, UnitBufs &ub, int *cnt, ResultSet &R) -> int {
 		int c0 = 0;
 		while (c0 < nc) {
 			std::vector<long long> scrOff, predOff;
@@ -423,9 +437,9 @@ int psc_solve(psc_ctx *ctx)
 			CK(cudaMemsetAsync(ch.n_exon, 0, sizeof(int) * (size_t)nUnits, strm));
 			long long *unitDbg = nullptr;
 			if (getenv("PSC_DEBUG_UNITS")) {
-				if (!st.dp_dbg.ensure(sizeof(long long) * 3 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
-				CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 3 * (size_t)(nUnits + 1), strm));
-				unitDbg = st.dp_dbg.as<long long>();
+				if (!ub.dbg.ensure(sizeof(long long) * 3 * (size_t)(nUnits + 1))) return ctx->fail("out of device memory");
+				CK(cudaMemsetAsync(ub.dbg.p, 0, sizeof(long long) * 3 * (size_t)(nUnits + 1), strm));
+				unitDbg = ub.dbg.as<long long>();
 			}
 			for (int phase = 1; phase <= 3; ++phase) {
 				CK(cudaMemsetAsync(cnt, 0, 32, strm));
@@ -495,26 +509,26 @@ int psc_solve(psc_ctx *ctx)
 				           ub.order.as<int>(), nList, cnt, ctx->coop);
 				++launches;
 				CK(cudaGetLastError());
-				size_t t0 = st.r_comp.size(), e0 = st.r_exon_start.size();
-				st.r_comp.resize(t0 + (size_t)nt); st.r_sample.resize(t0 + (size_t)nt); st.r_chr.resize(t0 + (size_t)nt);
-				st.r_gene.resize(t0 + (size_t)nt); st.r_strand.resize(t0 + (size_t)nt); st.r_fpkm.resize(t0 + (size_t)nt);
-				st.r_cov.resize(t0 + (size_t)nt); st.r_exon_start.resize(e0 + (size_t)ne); st.r_exon_end.resize(e0 + (size_t)ne);
+				size_t t0 = R.r_comp.size(), e0 = R.r_exon_start.size();
+				R.r_comp.resize(t0 + (size_t)nt); R.r_sample.resize(t0 + (size_t)nt); R.r_chr.resize(t0 + (size_t)nt);
+				R.r_gene.resize(t0 + (size_t)nt); R.r_strand.resize(t0 + (size_t)nt); R.r_fpkm.resize(t0 + (size_t)nt);
+				R.r_cov.resize(t0 + (size_t)nt); R.r_exon_start.resize(e0 + (size_t)ne); R.r_exon_end.resize(e0 + (size_t)ne);
 				std::vector<long long> eo((size_t)nt);
-				CK(cudaMemcpyAsync(st.r_comp.data() + t0, o.comp, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(st.r_sample.data() + t0, o.sample, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(st.r_chr.data() + t0, o.chr, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(st.r_gene.data() + t0, o.gene, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(st.r_strand.data() + t0, o.strand, (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(st.r_fpkm.data() + t0, o.fpkm, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(st.r_cov.data() + t0, o.cov, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_comp.data() + t0, o.comp, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_sample.data() + t0, o.sample, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_chr.data() + t0, o.chr, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_gene.data() + t0, o.gene, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_strand.data() + t0, o.strand, (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_fpkm.data() + t0, o.fpkm, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_cov.data() + t0, o.cov, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
 				CK(cudaMemcpyAsync(eo.data(), o.exon_off, sizeof(long long) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(st.r_exon_start.data() + e0, o.exon_start, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(st.r_exon_end.data() + e0, o.exon_end, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_exon_start.data() + e0, o.exon_start, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(R.r_exon_end.data() + e0, o.exon_end, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, strm));
 				CK(cudaStreamSynchronize(strm));
 				lap("emit + copy back");
-				st.r_exon_off.pop_back();
-				for (long long k = 0; k < nt; ++k) st.r_exon_off.push_back((long long)e0 + eo[(size_t)k]);
-				st.r_exon_off.push_back((long long)e0 + ne);
+				R.r_exon_off.pop_back();
+				for (long long k = 0; k < nt; ++k) R.r_exon_off.push_back((long long)e0 + eo[(size_t)k]);
+				R.r_exon_off.push_back((long long)e0 + ne);
 			}
 			c0 = c1;
 		}
@@ -601,11 +615,14 @@ int psc_solve(psc_ctx *ctx)
 			long long *dbgPtr = dpDbg ? st.dp_dbg.as<long long>() : nullptr;
 #ifndef PSC_CPU_SHIM
 			CK(cudaFuncSetAttribute(k_dp_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PSC_DP_SMEM_PER_WARP));
+			{
+			std::lock_guard<std::mutex> lk_(ctx->launchMu);
 			ctx->ktime_begin(4, strm);
 			k_dp_units<<<launch_grid(ctx, nRedo), 128, 4 * smemPerWarp, strm>>>(
 			    ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nRedo, (char *)(*db.scratch).p, (char *)db.dp_tx.p,
 			    db.dp_ntx.as<int>(), cnt, ctx->coop, smemPerWarp, dbgPtr);
 			ctx->ktime_end();
+			}
 #else
 			KLAUNCH_ON(strm, 4, k_dp_units, launch_grid(ctx, nRedo), 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nRedo,
 			           (char *)(*db.scratch).p, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, ctx->coop, smemPerWarp, dbgPtr);
@@ -650,7 +667,7 @@ int psc_solve(psc_ctx *ctx)
 		return 0;
 	};
 	// issues the DP of `comps` chunk by chunk; all chunks but the last are finished here, the last one is left in `pd`
-	auto dp_launch = [&](const std::vector<int> &comps, cudaStream_t strm, DpBufs &db, int *cnt, DpPending &pd) -> int {
+	auto dp_launch = [&](const std::vector<int> &comps, cudaStream_t strm, DpBufs &db, int *cnt, DpPending &pd, bool heavyLaunch) -> int {
 		size_t i0 = 0;
 		while (i0 < comps.size()) {
 			if (pd.active) {
@@ -661,7 +678,7 @@ int psc_solve(psc_ctx *ctx)
 			pd.mergeOff.clear();
 			std::vector<long long> cost;
 			long long tAcc = 0, mAcc = 0;
-			size_t arenaBytes = 0;
+			size_t arenaBytes = 0, hotWanted = 0;
 			size_t i1 = i0;
 			while (i1 < comps.size()) {
 				int c = comps[i1];
@@ -701,7 +718,8 @@ int psc_solve(psc_ctx *ctx)
 					u.scratch_off = 0;
 					u.tx_off = tAcc + tNeed;
 					tNeed += (long long)dp_txlist_layout(nullptr, nullptr, u.iterBound, W);
-					aNeed = std::max(aNeed, dp2_layout(nullptr, nullptr, nullptr, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100), 0));
+					aNeed = std::max(aNeed, dp2_layout(nullptr, nullptr, nullptr, 0, nullptr, 0, n, ctx->h_next_cnt[(size_t)c], std::max(C, 100)));
+					hotWanted = std::max(hotWanted, dp2_smem_wanted(n));
 					mine.push_back(u);
 				}
 				long long mNeed = (long long)dp_merge_layout(nullptr, nullptr, W, cap);
@@ -725,17 +743,42 @@ int psc_solve(psc_ctx *ctx)
 			std::vector<int> order((size_t)nUnits);
 			for (int u = 0; u < nUnits; ++u) order[(size_t)u] = u;
 			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
-			// one arena per cooperative group of the grid; fewer groups when the arenas would not fit the budget
+			// one arena per cooperative group of the grid; fewer groups when the arenas would not fit the budget.
+			// Shared memory: four units per block with a 16 KB slice each (PSC_DP_SMEM_KB overrides).  The launch over the
+			// heavy components additionally hands its nCrit most expensive units to the critical stream: one unit per
+			// block, with room for the biggest program, on the SMs reserved for them when the device is partitioned.
 			arenaBytes = (arenaBytes + 255) & ~(size_t)255;
-			const long long groupsPerBlock = 128 / ctx->coop;
-			long long blocks = (nUnits + groupsPerBlock - 1) / groupsPerBlock;
-			blocks = std::min<long long>(blocks, (long long)ctx->n_sm * PSC_DP2_MINBLOCKS);
+			const int threads = 128;
+			size_t hotBytes = 0, hotCrit = 0;
+			int nCrit = 0;
+			if (ctx->coop == 32) {
+				hotBytes = std::min<size_t>((hotWanted + 1023) & ~(size_t)1023, 16 << 10);
+				if (const char *e = getenv("PSC_DP_SMEM_KB")) hotBytes = (size_t)std::max(0, atoi(e)) << 10;
+				if (heavyLaunch && useV2 && !dpDbg) {
+					nCrit = 64;
+					if (const char *e = getenv("PSC_DP_CRIT")) nCrit = std::max(0, atoi(e));
+					nCrit = std::min(nCrit, nUnits / 2);
+					if (strm == ctx->sCrit) nCrit = nUnits; // the launch already lives in the critical partition: every unit takes that shape
+					for (int k = 0; k < nCrit; ++k) {
+						int c = pd.units[(size_t)order[(size_t)k]].comp;
+						hotCrit = std::max(hotCrit, dp2_smem_wanted(ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c]));
+					}
+					hotCrit = std::min<size_t>((hotCrit + 1023) & ~(size_t)1023, 110 << 10);
+				}
+			}
+			const long long groupsPerBlock = threads / ctx->coop;
+			const int nBulk = nUnits - nCrit;
+			long long blocks = (nBulk + groupsPerBlock - 1) / groupsPerBlock;
 			{
+				long long blocksPerSm = PSC_DP2_MINBLOCKS;
+				if (hotBytes > 0) blocksPerSm = std::max<long long>(1, std::min<long long>(blocksPerSm, (long long)((227 << 10) / (hotBytes * 4 + 1024))));
+				blocks = std::min<long long>(blocks, (long long)ctx->n_sm * blocksPerSm);
 				long long fit = (long long)(ctx->mem_budget / (arenaBytes * (size_t)groupsPerBlock));
 				blocks = std::max<long long>(1, std::min(blocks, fit));
 			}
+			const size_t bulkArenas = (size_t)blocks * (size_t)groupsPerBlock;
 			if (!db.dp_tx.ensure((size_t)tAcc + 16) || !db.dp_ntx.ensure(sizeof(int) * (size_t)(nUnits + 1)) || !db.dp_ovf.ensure(64) ||
-			    !db.dp_arena.ensure((size_t)blocks * (size_t)groupsPerBlock * arenaBytes + 16))
+			    !db.dp_arena.ensure((bulkArenas + (size_t)nCrit) * arenaBytes + 16))
 				return ctx->fail("out of device memory (DP program arenas)");
 			CK(cudaMemsetAsync(db.dp_ntx.p, useV2 ? 0 : 0xff, sizeof(int) * (size_t)(nUnits + 1), strm));
 			CK(cudaMemsetAsync(db.dp_ovf.p, 0, 64, strm));
@@ -750,8 +793,33 @@ int psc_solve(psc_ctx *ctx)
 				dbgPtr = st.dp_dbg.as<long long>();
 			}
 			if (useV2) {
-				KLAUNCH_ON(strm, 10, k_dp2_units, (int)blocks, 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits,
-				           (char *)db.dp_arena.p, arenaBytes, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, db.dp_ovf.as<int>(), ctx->coop, dbgPtr);
+#ifndef PSC_CPU_SHIM
+				CK(cudaFuncSetAttribute(k_dp2_units, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 << 10));
+				std::lock_guard<std::mutex> lk_(ctx->launchMu);
+				if (nCrit > 0) {
+					// the critical units: the setup above must be visible to their stream, and the merge waits for them
+					CK(cudaEventRecord(ctx->evCritGo, strm));
+					CK(cudaStreamWaitEvent(ctx->sCrit, ctx->evCritGo, 0));
+					ctx->ktime_begin(10, ctx->sCrit);
+					k_dp2_units<<<nCrit, 32, hotCrit, ctx->sCrit>>>(ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nCrit,
+					                                              (char *)db.dp_arena.p + bulkArenas * arenaBytes, arenaBytes, hotCrit, (char *)db.dp_tx.p,
+					                                              db.dp_ntx.as<int>(), cnt + 4, db.dp_ovf.as<int>(), ctx->coop, dbgPtr);
+					ctx->ktime_end();
+					CK(cudaEventRecord(ctx->evCritDone, ctx->sCrit));
+					++launches;
+				}
+				if (nBulk > 0) {
+					ctx->ktime_begin(10, strm);
+					k_dp2_units<<<(int)blocks, threads, hotBytes * (size_t)(threads / 32), strm>>>(
+					    ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>() + nCrit, nBulk, (char *)db.dp_arena.p, arenaBytes, hotBytes,
+					    (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, db.dp_ovf.as<int>(), ctx->coop, dbgPtr);
+					ctx->ktime_end();
+				}
+				if (nCrit > 0) CK(cudaStreamWaitEvent(strm, ctx->evCritDone, 0));
+#else
+				KLAUNCH_ON(strm, 10, k_dp2_units, (int)blocks, threads, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits,
+				           (char *)db.dp_arena.p, arenaBytes, hotBytes, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, db.dp_ovf.as<int>(), ctx->coop, dbgPtr);
+#endif
 				++launches;
 				CK(cudaGetLastError());
 			} else {
@@ -781,7 +849,11 @@ int psc_solve(psc_ctx *ctx)
 				byC.push_back({-Cmax, c});
 			}
 			std::sort(byC.begin(), byC.end());
+			// the heavy chain runs in the critical SM partition: as many components as keep its (component, sample) units
+			// at about four per critical SM (PSC_HEAVY_COMPS overrides); without partitioning, 1/16 of the DP components
 			size_t nH = std::min<size_t>(std::max<size_t>(dpList.size() / 16, 1), (size_t)ctx->n_sm);
+			if (ctx->critSms > 0) nH = std::max<size_t>(1, std::min<size_t>(nH, (size_t)(4 * ctx->critSms / std::max(1, S))));
+			if (const char *e = getenv("PSC_HEAVY_COMPS")) nH = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), dpList.size() - 1));
 			if (forced && dpList.size() < 64) nH = std::max<size_t>(dpList.size() / 4, 1);
 			std::vector<char> isH((size_t)nc, 0);
 			for (size_t k = 0; k < nH; ++k) isH[(size_t)byC[k].second] = 1;
@@ -789,36 +861,69 @@ int psc_solve(psc_ctx *ctx)
 			for (int c : heavy) group[(size_t)c] = 2;
 		}
 	}
-	size_t pass1Tx = 0;
-	bool twoPasses = false;
+	// n_cand of the components of `comps`, copied from the device on `strm` (the two chains own disjoint components)
+	auto fetch_n_cand = [&](const std::vector<int> &comps, cudaStream_t strm) -> int {
+		std::vector<int> tmp((size_t)nc);
+		CK(cudaMemcpyAsync(tmp.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, strm));
+		CK(cudaStreamSynchronize(strm));
+		for (int c : comps) st.h_n_cand[(size_t)c] = tmp[(size_t)c];
+		return 0;
+	};
 	if (!heavy.empty()) {
+		// Two chains, each driven by its own host thread so that neither waits for the other's synchronisation points:
+		// [main stream]   heavy DP -> merge -> pick / refine / EM / emit of the heavy components
+		// [second stream] DP of the rest -> merge -> pick / refine / EM / emit of every other component
 		DpPending pdH, pdR;
-		if (dp_launch(heavy, ctx->stream, st.db[0], counter, pdH) != 0) return 1;
-		if (dp_launch(rest, ctx->stream2, st.db[1], counter + 8, pdR) != 0) return 1;
-		if (dp_finish(pdR, ctx->stream2, st.db[1], counter + 8) != 0) return 1;
-		CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream2));
-		CK(cudaStreamSynchronize(ctx->stream2));
-		lap("dp merge (second stream)");
-		if (run_units(1, ctx->stream2, st.ub[1], counter + 8) != 0) return 1;
-		pass1Tx = st.r_comp.size();
-		twoPasses = true;
-		lap("second stream (rest of DP, other components)");
-		if (dp_finish(pdH, ctx->stream, st.db[0], counter) != 0) return 1;
-		lap("heavy DP tail");
-	} else if (!dpList.empty()) {
-		DpPending pd;
-		if (dp_launch(dpList, ctx->stream, st.db[1], counter, pd) != 0) return 1;
-		if (dp_finish(pd, ctx->stream, st.db[1], counter) != 0) return 1;
+		// with SM partitioning the whole heavy chain lives in the critical partition
+		const cudaStream_t sHeavy = ctx->critSms > 0 ? ctx->sCrit : ctx->sMain;
+		if (dp_launch(heavy, sHeavy, st.db[0], counter, pdH, true) != 0) return 1;
+		if (dp_launch(rest, ctx->sSecond, st.db[1], counter + 8, pdR, false) != 0) return 1;
+		ResultSet resR;
+		resR.reset();
+		int rcR = 0;
+		std::thread second([&]() {
+			cudaSetDevice(ctx->device);
+			rcR = [&]() -> int {
+				if (dp_finish(pdR, ctx->sSecond, st.db[1], counter + 8) != 0) return 1;
+				if (fetch_n_cand(rest, ctx->sSecond) != 0) return 1;
+				lap("dp merge (second stream)");
+				if (run_units(1, ctx->sSecond, st.ub[1], counter + 8, resR) != 0) return 1;
+				lap("second stream done");
+				return 0;
+			}();
+		});
+		int rcH = [&]() -> int {
+			if (dp_finish(pdH, sHeavy, st.db[0], counter) != 0) return 1;
+			if (fetch_n_cand(heavy, sHeavy) != 0) return 1;
+			lap("heavy dp merge");
+			return run_units(2, sHeavy, st.ub[0], counter, st);
+		}();
+		second.join();
+		if (rcH != 0 || rcR != 0) return 1;
+		lap("both chains done");
+		// pass 1 first, then pass 2, then one component-major list
+		ResultSet resH;
+		resH.reset();
+		std::swap(static_cast<ResultSet &>(st), resH);
+		st.reset();
+		st.append(resR);
+		const size_t pass1Tx = st.r_comp.size();
+		st.append(resH);
+		merge_passes(st, pass1Tx);
+	} else {
+		if (!dpList.empty()) {
+			DpPending pd;
+			if (dp_launch(dpList, ctx->sMain, st.db[1], counter, pd, false) != 0) return 1;
+			if (dp_finish(pd, ctx->sMain, st.db[1], counter) != 0) return 1;
+			if (fetch_n_cand(dpList, ctx->sMain) != 0) return 1;
+		}
+		if (run_units(0, ctx->sMain, st.ub[0], counter, st) != 0) return 1;
 	}
-	CK(cudaMemcpyAsync(st.h_n_cand.data(), sv.n_cand, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
-	if (run_units(twoPasses ? 2 : 0, ctx->stream, st.ub[0], counter) != 0) return 1;
-	if (twoPasses) merge_passes(st, pass1Tx);
 	lap("exon offsets");
 	int herr = 0;
-	CK(cudaMemcpyAsync(&herr, sv.error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaEventRecord(ctx->ev1, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpyAsync(&herr, sv.error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->sMain));
+	CK(cudaEventRecord(ctx->ev1, ctx->sMain));
+	CK(cudaStreamSynchronize(ctx->sMain));
 	if (herr != 0) return ctx->fail("device-side capacity error " + std::to_string(herr));
 	float ms = 0;
 	cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);

@@ -3,11 +3,11 @@
 // device buffers of one pass of the per-unit kernels (pick / refine / EM / emit).  Two sets: the pass over
 // the enumerated components runs on its own stream while the DP kernel is still busy on the main one.
 struct UnitBufs {
-	DevBuf scr_off, scratch, pred_off, pred, n_pred, n_raw, n_exon, order, tx_off, ex_off;
+	DevBuf scr_off, scratch, pred_off, pred, n_pred, n_raw, n_exon, order, tx_off, ex_off, dbg;
 	DevBuf o_comp, o_sample, o_chr, o_gene, o_strand, o_exon_off, o_exon_start, o_exon_end, o_fpkm, o_cov;
 	void release()
 	{
-		DevBuf *all[] = {&scr_off, &scratch, &pred_off, &pred, &n_pred, &n_raw, &n_exon, &order, &tx_off, &ex_off, &o_comp,
+		DevBuf *all[] = {&scr_off, &scratch, &pred_off, &pred, &n_pred, &n_raw, &n_exon, &order, &tx_off, &ex_off, &dbg, &o_comp,
 		                 &o_sample, &o_chr, &o_gene, &o_strand, &o_exon_off, &o_exon_start, &o_exon_end, &o_fpkm, &o_cov};
 		for (DevBuf *b : all) b->release();
 	}
@@ -24,30 +24,54 @@ struct DpBufs {
 	}
 };
 
-struct SolveState {
-	DevBuf can_start, can_end, edge_support, cs00, at_cnt, use_dp, def_gene, n_cand, cand_row_off, cand_bits_off,
-	    cand_bits, cand_first, cand_last, cand_corr, cand_sup1, cand_sup2, error_flag, fscratch, fs_off, list, stk, dp_dbg,
-	    dp_heavy_scratch;
-	UnitBufs ub[2];
-	// db[0]: the heavy DP components (own scratch); db[1]: the others, in ub[0].scratch (that DP is over before
-	// the pass that uses ub[0] starts)
-	DpBufs db[2];
-	SolveState()
-	{
-		db[0].scratch = &dp_heavy_scratch;
-		db[1].scratch = &ub[0].scratch;
-	}
-	std::vector<int> h_at_cnt, h_use_dp, h_n_cand;
-	// results, host side (filled chunk by chunk)
+// transcripts copied back to the host, in the order the passes produced them
+struct ResultSet {
 	std::vector<int> r_comp, r_sample, r_chr, r_gene, r_exon_start, r_exon_end;
 	std::vector<int8_t> r_strand;
 	std::vector<long long> r_exon_off;
 	std::vector<double> r_fpkm, r_cov;
+	void reset()
+	{
+		r_comp.clear(); r_sample.clear(); r_chr.clear(); r_gene.clear(); r_strand.clear();
+		r_exon_off.assign(1, 0); r_exon_start.clear(); r_exon_end.clear(); r_fpkm.clear(); r_cov.clear();
+	}
+	// appends `o` behind this set
+	void append(const ResultSet &o)
+	{
+		const long long e0 = (long long)r_exon_start.size();
+		r_comp.insert(r_comp.end(), o.r_comp.begin(), o.r_comp.end());
+		r_sample.insert(r_sample.end(), o.r_sample.begin(), o.r_sample.end());
+		r_chr.insert(r_chr.end(), o.r_chr.begin(), o.r_chr.end());
+		r_gene.insert(r_gene.end(), o.r_gene.begin(), o.r_gene.end());
+		r_strand.insert(r_strand.end(), o.r_strand.begin(), o.r_strand.end());
+		r_fpkm.insert(r_fpkm.end(), o.r_fpkm.begin(), o.r_fpkm.end());
+		r_cov.insert(r_cov.end(), o.r_cov.begin(), o.r_cov.end());
+		r_exon_start.insert(r_exon_start.end(), o.r_exon_start.begin(), o.r_exon_start.end());
+		r_exon_end.insert(r_exon_end.end(), o.r_exon_end.begin(), o.r_exon_end.end());
+		r_exon_off.pop_back();
+		for (size_t k = 0; k < o.r_exon_off.size(); ++k) r_exon_off.push_back(e0 + o.r_exon_off[k]);
+	}
+};
+
+struct SolveState : ResultSet {
+	DevBuf can_start, can_end, edge_support, cs00, at_cnt, use_dp, def_gene, n_cand, cand_row_off, cand_bits_off,
+	    cand_bits, cand_first, cand_last, cand_corr, cand_sup1, cand_sup2, error_flag, fscratch, fs_off, list, stk, dp_dbg,
+	    dp_heavy_scratch, dp_rest_scratch;
+	UnitBufs ub[2];
+	// db[0]: the heavy DP components; db[1]: the others.  The scratch buffers are only used by the walk-engine fallback.
+	DpBufs db[2];
+	SolveState()
+	{
+		db[0].scratch = &dp_heavy_scratch;
+		db[1].scratch = &dp_rest_scratch;
+	}
+	std::vector<int> h_at_cnt, h_use_dp, h_n_cand;
+	// results, host side (filled chunk by chunk): the ResultSet base
 	void release()
 	{
 		DevBuf *all[] = {&can_start, &can_end, &edge_support, &cs00, &at_cnt, &use_dp, &def_gene, &n_cand,
 		                 &cand_row_off, &cand_bits_off, &cand_bits, &cand_first, &cand_last, &cand_corr, &cand_sup1,
-		                 &cand_sup2, &error_flag, &fscratch, &fs_off, &list, &stk, &dp_dbg, &dp_heavy_scratch};
+		                 &cand_sup2, &error_flag, &fscratch, &fs_off, &list, &stk, &dp_dbg, &dp_heavy_scratch, &dp_rest_scratch};
 		for (DevBuf *b : all) b->release();
 		ub[0].release();
 		ub[1].release();

@@ -47,6 +47,9 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = 0; return 0; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = 0; return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
