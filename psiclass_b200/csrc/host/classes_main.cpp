@@ -39,7 +39,9 @@ static const char usage[] =
     "\t--stranded STRING: un/rf/fr for library unstranded/fr-firstand/fr-secondstrand (default: not used)\n"
     "\t--hasMateIdSuffix: the read id has suffix such as .1, .2 for a mate pair. (default: false)\n"
     "\t--maxDpConstraintSize: the maximum number of subexons a constraint can cover in dynamic programming. (default: 7; -1 for inf)\n"
-    "\t--primaryParalog: use primary alignment to retain paralog genes instead of unique alignments. (default: not used)\n";
+    "\t--primaryParalog: use primary alignment to retain paralog genes instead of unique alignments. (default: not used)\n"
+    "\t--vote STRING: also write the stage-4 vote (what vote-transcripts would make of the GTFs) to this file. (default: not used)\n"
+    "\t--vote-depth FLOAT: vote-transcripts' -d. (default: 1)\n";
 
 static const char *short_options = "s:b:f:o:d:p:c:h";
 static struct option long_options[] = {{"ls", required_argument, 0, 10000},
@@ -48,6 +50,8 @@ static struct option long_options[] = {{"ls", required_argument, 0, 10000},
                                        {"primaryParalog", no_argument, 0, 10003},
                                        {"maxDpConstraintSize", required_argument, 0, 10004},
                                        {"stranded", required_argument, 0, 10005},
+                                       {"vote", required_argument, 0, 10006},
+                                       {"vote-depth", required_argument, 0, 10007},
                                        {(char *)0, 0, 0, 0}};
 
 struct Shard {
@@ -207,6 +211,8 @@ int main(int argc, char *argv[])
 	double fpkmFraction = 0.05, classifierThreshold = 0.05, minDepth = 2.5;
 	int numThreads = 1, maxDp = 7;
 	bool primaryParalog = false;
+	std::string votePath;
+	double voteDepth = 1.0;
 	int c, option_index = 0;
 	while ((c = getopt_long(argc, argv, short_options, long_options, &option_index)) != -1) {
 		if (c == 's') subexonPath = optarg;
@@ -234,6 +240,8 @@ int main(int argc, char *argv[])
 		else if (c == 10003) primaryParalog = true;
 		else if (c == 10004) maxDp = atoi(optarg);
 		else if (c == 10005) { /* --stranded only changes stages 0-2 (Q13) */ }
+		else if (c == 10006) votePath = optarg;
+		else if (c == 10007) voteDepth = atof(optarg);
 		else {
 			printf("%s", usage);
 			exit(1);
@@ -375,9 +383,20 @@ int main(int argc, char *argv[])
 		int64_t x = last_read(s, g.n_comp - 1);
 		totalReadCnt[(size_t)s] = x < sr.n_reads() ? (double)sr.prim_cum[(size_t)x] : (double)sr.total_primary;
 	}
-	if (!psc::write_gtfs(queue, totalReadCnt, g.chr_names, prefix, argc, argv, bamPaths, err)) {
+	std::vector<psc::VoteTx> voteTx;
+	if (!psc::write_gtfs(queue, totalReadCnt, g.chr_names, prefix, argc, argv, bamPaths, err, votePath.empty() ? nullptr : &voteTx)) {
 		printf("%s\n", err.c_str());
 		exit(1);
+	}
+	const double tGtf = now_s();
+	if (!votePath.empty()) { // stage 4 fused: Vote.cpp on the transcripts in memory
+		FILE *fp = fopen(votePath.c_str(), "w");
+		if (!fp) {
+			printf("Cannot write %s.\n", votePath.c_str());
+			exit(1);
+		}
+		psc::vote_core(voteTx, S, voteDepth, fp);
+		fclose(fp);
 	}
 	if (const char *pj = getenv("PSC_PERF_JSON")) { // wall-clock of the phases, for bench.py (path of the file to write)
 		if (FILE *fp = fopen(pj, "w")) {
@@ -391,9 +410,9 @@ int main(int argc, char *argv[])
 			for (auto &sr : samples) nReads += sr.n_reads();
 			const double tEnd = now_s();
 			fprintf(fp, "{\"components\": %d, \"samples\": %d, \"gpus\": %d, \"host_threads\": %d, \"reads\": %lld, \"bam_bytes\": %lld, "
-			            "\"decode_s\": %.4f, \"decode_MBps\": %.1f, \"graph_s\": %.4f, \"device_s\": %.4f, \"gtf_s\": %.4f, \"total_s\": %.4f, \"shards\": [",
+			            "\"decode_s\": %.4f, \"decode_MBps\": %.1f, \"graph_s\": %.4f, \"device_s\": %.4f, \"gtf_s\": %.4f, \"vote_s\": %.4f, \"total_s\": %.4f, \"shards\": [",
 			        g.n_comp, S, nGpu, numThreads, nReads, bamBytes, tDecoded - tStart, bamBytes / 1e6 / std::max(1e-9, tDecoded - tStart),
-			        tGraph - tDecoded, tDevice - tGraph, tEnd - tDevice, tEnd - tStart);
+			        tGraph - tDecoded, tDevice - tGraph, tGtf - tDevice, tEnd - tGtf, tEnd - tStart);
 			for (size_t d = 0; d < shards.size(); ++d)
 				fprintf(fp, "%s{\"components\": %d, \"reads\": %lld, \"upload_s\": %.4f, \"constraints_s\": %.4f, \"solve_s\": %.4f, \"download_s\": %.4f}",
 				        d ? ", " : "", shards[d].c1 - shards[d].c0, shards[d].n_reads, shards[d].upload_s, shards[d].constraints_s,

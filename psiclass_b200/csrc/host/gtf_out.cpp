@@ -18,7 +18,8 @@ static int cmp_tx(const OutTx &a, const OutTx &b)
 }
 
 bool write_gtfs(std::vector<OutTx> &q, const std::vector<double> &totalReadCnt, const std::vector<std::string> &chr,
-                const std::string &prefix, int argc, char **argv, const std::vector<std::string> &bams, std::string &err)
+                const std::string &prefix, int argc, char **argv, const std::vector<std::string> &bams, std::string &err,
+                std::vector<VoteTx> *forVote)
 {
 	size_t S = bams.size();
 	// ComputeFPKMTPM: per-sample sums run in queue order
@@ -49,6 +50,7 @@ bool write_gtfs(std::vector<OutTx> &q, const std::vector<double> &totalReadCnt, 
 		const char *base = strrchr(bams[s].c_str(), '/');
 		fprintf(fps[s], "#%s\n", base ? base + 1 : bams[s].c_str());
 	}
+	std::vector<std::vector<VoteTx>> perSample(forVote ? S : 0);
 	int gid = -1, tid = 0;
 	for (size_t i = 0; i < order.size();) {
 		size_t j = i + 1;
@@ -67,10 +69,26 @@ bool write_gtfs(std::vector<OutTx> &q, const std::vector<double> &totalReadCnt, 
 			for (size_t e = 0; e < t.exons.size(); ++e)
 				fprintf(fp, "%s\tPsiCLASS\texon\t%d\t%d\t1000\t%c\t.\tgene_id \"%s.%d\"; transcript_id \"%s.%d.%d\"; exon_number \"%d\"; FPKM \"%.6lf\"; TPM \"%.6lf\"; cov \"%.6lf\";\n",
 				        c, t.exons[e].first, t.exons[e].second, t.strand, c, t.gene_id, c, t.gene_id, tid, (int)e + 1, t.fpkm, t.tpm, t.cov);
+			if (forVote) {
+				VoteTx v;
+				v.sample = t.sample;
+				v.gene_id = t.gene_id;
+				v.transcript_id = tid;
+				v.chrom = c;
+				v.strand = t.strand;
+				v.exons = t.exons;
+				v.fpkm = gtf_rounded(t.fpkm);
+				v.tpm = gtf_rounded(t.tpm);
+				v.cov = gtf_rounded(t.cov);
+				perSample[(size_t)t.sample].push_back(std::move(v));
+			}
 		}
 		i = j;
 	}
 	for (FILE *fp : fps) fclose(fp);
+	if (forVote)
+		for (auto &ps : perSample)
+			for (auto &v : ps) forVote->push_back(std::move(v));
 	return true;
 }
 

@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include "vote.h"
+
 namespace psc {
 
 struct OutTx {
@@ -19,6 +21,8 @@ struct OutTx {
 // total_read_cnt[s] is Alignments::totalReadCnt of sample s when the stream stopped (Q8).
 bool write_gtfs(std::vector<OutTx> &queue, const std::vector<double> &total_read_cnt,
                 const std::vector<std::string> &chr_names, const std::string &prefix, int argc, char **argv,
-                const std::vector<std::string> &bam_paths, std::string &err);
+                const std::vector<std::string> &bam_paths, std::string &err, std::vector<VoteTx> *for_vote = nullptr);
+// for_vote: when given, receives what vote-transcripts would parse back from the files just written (sample by
+// sample, in file order, numbers rounded to the six printed decimals) -- the fused stage 3 -> stage 4 hand-over
 
 } // namespace psc

@@ -96,6 +96,29 @@ struct DevBuf {
 	template <class T> T *as() { return (T *)p; }
 };
 
+// pinned host staging memory (device -> host copies of results run at full PCIe speed only from pinned memory)
+struct HostBuf {
+	void *p = nullptr;
+	size_t bytes = 0;
+	bool ensure(size_t n)
+	{
+		if (n <= bytes && p) return true;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		bytes = 0;
+		size_t want = n + n / 4 + 4096;
+		if (cudaMallocHost(&p, want) != cudaSuccess) return false;
+		bytes = want;
+		return true;
+	}
+	void release()
+	{
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		bytes = 0;
+	}
+};
+
 #include "psc_solve_state.h"
 
 __global__ void k_pow_quarter(const double *x, double *y, long long n)

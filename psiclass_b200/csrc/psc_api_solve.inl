@@ -160,46 +160,49 @@ __global__ void __launch_bounds__(128) k_emit(GraphDev g, SolveDev sv, ChunkDev 
 	}
 }
 
-// psc_solve may run the per-unit kernels in two passes (enumerated components, then DP components); each pass
-// appends its transcripts in component order.  Restore the single component-major order the C ABI promises.
-static void merge_passes(SolveState &st, size_t nA)
+// psc_solve runs the per-unit kernels as two passes over disjoint sets of components (the bulk, the heavy DP
+// components); each pass delivers its transcripts in component order.  Merge the two lists into the single
+// component-major order the C ABI promises: one pass over the data, split over a few host threads.
+static void merge_passes(ResultSet &out, const ResultSet &A, const ResultSet &B)
 {
-	const size_t nt = st.r_comp.size();
-	if (nA == 0 || nA == nt) return;
-	std::vector<size_t> perm(nt);
+	const size_t nA = A.r_comp.size(), nB = B.r_comp.size(), nt = nA + nB;
+	// source of output position k: index into A, or nA + index into B
+	std::vector<uint32_t> perm(nt);
 	{
-		size_t a = 0, b = nA, k = 0;
-		while (a < nA && b < nt) perm[k++] = st.r_comp[a] < st.r_comp[b] ? a++ : b++;
-		while (a < nA) perm[k++] = a++;
-		while (b < nt) perm[k++] = b++;
+		size_t a = 0, b = 0, k = 0;
+		while (a < nA && b < nB) perm[k++] = A.r_comp[a] < B.r_comp[b] ? (uint32_t)a++ : (uint32_t)(nA + b++);
+		while (a < nA) perm[k++] = (uint32_t)a++;
+		while (b < nB) perm[k++] = (uint32_t)(nA + b++);
 	}
-	// new exon offsets (sequential prefix), then the gathers split over a few host threads by output range
-	std::vector<long long> off(nt + 1);
+	out.r_exon_off.resize(nt + 1);
 	{
 		long long e = 0;
 		for (size_t k = 0; k < nt; ++k) {
-			off[k] = e;
-			e += st.r_exon_off[perm[k] + 1] - st.r_exon_off[perm[k]];
+			out.r_exon_off[k] = e;
+			size_t p = perm[k];
+			e += p < nA ? A.r_exon_off[p + 1] - A.r_exon_off[p] : B.r_exon_off[p - nA + 1] - B.r_exon_off[p - nA];
 		}
-		off[nt] = e;
+		out.r_exon_off[nt] = e;
 	}
-	std::vector<int> comp(nt), sample(nt), chr(nt), gene(nt), es(st.r_exon_start.size()), ee(st.r_exon_end.size());
-	std::vector<int8_t> strand(nt);
-	std::vector<double> fpkm(nt), cov(nt);
+	const size_t ne = (size_t)out.r_exon_off[nt];
+	out.r_comp.resize(nt); out.r_sample.resize(nt); out.r_chr.resize(nt); out.r_gene.resize(nt); out.r_strand.resize(nt);
+	out.r_fpkm.resize(nt); out.r_cov.resize(nt); out.r_exon_start.resize(ne); out.r_exon_end.resize(ne);
 	auto work = [&](size_t k0, size_t k1) {
 		for (size_t k = k0; k < k1; ++k) {
 			size_t p = perm[k];
-			comp[k] = st.r_comp[p];
-			sample[k] = st.r_sample[p];
-			chr[k] = st.r_chr[p];
-			gene[k] = st.r_gene[p];
-			strand[k] = st.r_strand[p];
-			fpkm[k] = st.r_fpkm[p];
-			cov[k] = st.r_cov[p];
-			long long s0 = st.r_exon_off[p], s1 = st.r_exon_off[p + 1], e = off[k];
-			for (long long q = s0; q < s1; ++q, ++e) {
-				es[(size_t)e] = st.r_exon_start[(size_t)q];
-				ee[(size_t)e] = st.r_exon_end[(size_t)q];
+			const ResultSet &R = p < nA ? A : B;
+			if (p >= nA) p -= nA;
+			out.r_comp[k] = R.r_comp[p];
+			out.r_sample[k] = R.r_sample[p];
+			out.r_chr[k] = R.r_chr[p];
+			out.r_gene[k] = R.r_gene[p];
+			out.r_strand[k] = R.r_strand[p];
+			out.r_fpkm[k] = R.r_fpkm[p];
+			out.r_cov[k] = R.r_cov[p];
+			const long long s0 = R.r_exon_off[p], n = R.r_exon_off[p + 1] - s0, e = out.r_exon_off[k];
+			if (n > 0) {
+				memcpy(&out.r_exon_start[(size_t)e], &R.r_exon_start[(size_t)s0], sizeof(int) * (size_t)n);
+				memcpy(&out.r_exon_end[(size_t)e], &R.r_exon_end[(size_t)s0], sizeof(int) * (size_t)n);
 			}
 		}
 	};
@@ -210,16 +213,6 @@ static void merge_passes(SolveState &st, size_t nA)
 	for (size_t t = 1; t < nThreads; ++t) pool.emplace_back(work, nt * t / nThreads, nt * (t + 1) / nThreads);
 	work(0, nt / nThreads);
 	for (auto &th : pool) th.join();
-	st.r_exon_off.swap(off);
-	st.r_exon_start.swap(es);
-	st.r_exon_end.swap(ee);
-	st.r_comp.swap(comp);
-	st.r_sample.swap(sample);
-	st.r_chr.swap(chr);
-	st.r_gene.swap(gene);
-	st.r_strand.swap(strand);
-	st.r_fpkm.swap(fpkm);
-	st.r_cov.swap(cov);
 }
 
 static int launch_grid(psc_ctx *ctx, long long units)
@@ -374,6 +367,34 @@ int psc_solve(psc_ctx *ctx)
 	// while the heavy DP units are still busy on the main one. ----
 	std::vector<char> group((size_t)nc, 0); // 2: heavy DP component
 	auto run_units = [&](int pass, cudaStream_t strm, UnitBufs &ub, int *cnt, ResultSet &R) -> int {
+		// per (component, sample) scratch needs of this pass, computed on a few host threads
+		std::vector<long long> soAll((size_t)nc * S, 0), poAll((size_t)nc * S, 0), sNeedAll((size_t)nc, 0), pNeedAll((size_t)nc, 0);
+		{
+			auto work = [&](int ca, int cb) {
+				for (int c = ca; c < cb; ++c) {
+					const bool mine = pass == 0 || (group[(size_t)c] == 2) == (pass == 2);
+					if (!mine) continue;
+					int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
+					int A = st.h_n_cand[(size_t)c];
+					long long sNeed = 0, pNeed = 0;
+					for (int s = 0; s < S; ++s) {
+						int M = ctx->samples[(size_t)s].h_npair[(size_t)c], C = ctx->samples[(size_t)s].h_ncon[(size_t)c];
+						int cap = std::max(1, std::min(A, M + 1));
+						soAll[(size_t)c * S + s] = sNeed;
+						poAll[(size_t)c * S + s] = pNeed;
+						sNeed += (long long)unit_scratch_layout(nullptr, nullptr, A, M, cap, n, C, ctx->h_comp_ng[(size_t)c], ctx->h_next_cnt[(size_t)c]);
+						pNeed += (long long)unit_pred_layout(nullptr, nullptr, cap);
+					}
+					sNeedAll[(size_t)c] = sNeed;
+					pNeedAll[(size_t)c] = pNeed;
+				}
+			};
+			const int nThreads = nc >= 8192 ? 4 : 1;
+			std::vector<std::thread> pool;
+			for (int t = 1; t < nThreads; ++t) pool.emplace_back(work, (int)((long long)nc * t / nThreads), (int)((long long)nc * (t + 1) / nThreads));
+			work(0, nc / nThreads);
+			for (auto &th : pool) th.join();
+		}
 		int c0 = 0;
 		while (c0 < nc) {
 			std::vector<long long> scrOff, predOff;
@@ -382,19 +403,10 @@ int psc_solve(psc_ctx *ctx)
 			long long sAcc = 0, pAcc = 0;
 			int c1 = c0;
 			while (c1 < nc) {
-				int n = ctx->h_comp_off[(size_t)c1 + 1] - ctx->h_comp_off[(size_t)c1];
 				int A = st.h_n_cand[(size_t)c1];
-				long long sNeed = 0, pNeed = 0;
-				std::vector<long long> so((size_t)S), po((size_t)S);
+				const long long sNeed = sNeedAll[(size_t)c1], pNeed = pNeedAll[(size_t)c1];
+				const long long *so = &soAll[(size_t)c1 * S], *po = &poAll[(size_t)c1 * S];
 				const bool mine = pass == 0 || (group[(size_t)c1] == 2) == (pass == 2);
-				for (int s = 0; s < S && mine; ++s) {
-					int M = ctx->samples[(size_t)s].h_npair[(size_t)c1], C = ctx->samples[(size_t)s].h_ncon[(size_t)c1];
-					int cap = std::max(1, std::min(A, M + 1));
-					so[(size_t)s] = sNeed;
-					po[(size_t)s] = pNeed;
-					sNeed += (long long)unit_scratch_layout(nullptr, nullptr, A, M, cap, n, C, ctx->h_comp_ng[(size_t)c1], ctx->h_next_cnt[(size_t)c1]);
-					pNeed += (long long)unit_pred_layout(nullptr, nullptr, cap);
-				}
 				if (c1 > c0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
 				for (int s = 0; s < S; ++s) {
 					scrOff.push_back(sAcc + so[(size_t)s]);
@@ -513,20 +525,40 @@ int psc_solve(psc_ctx *ctx)
 				R.r_comp.resize(t0 + (size_t)nt); R.r_sample.resize(t0 + (size_t)nt); R.r_chr.resize(t0 + (size_t)nt);
 				R.r_gene.resize(t0 + (size_t)nt); R.r_strand.resize(t0 + (size_t)nt); R.r_fpkm.resize(t0 + (size_t)nt);
 				R.r_cov.resize(t0 + (size_t)nt); R.r_exon_start.resize(e0 + (size_t)ne); R.r_exon_end.resize(e0 + (size_t)ne);
-				std::vector<long long> eo((size_t)nt);
-				CK(cudaMemcpyAsync(R.r_comp.data() + t0, o.comp, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(R.r_sample.data() + t0, o.sample, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(R.r_chr.data() + t0, o.chr, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(R.r_gene.data() + t0, o.gene, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(R.r_strand.data() + t0, o.strand, (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(R.r_fpkm.data() + t0, o.fpkm, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(R.r_cov.data() + t0, o.cov, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(eo.data(), o.exon_off, sizeof(long long) * (size_t)nt, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(R.r_exon_start.data() + e0, o.exon_start, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, strm));
-				CK(cudaMemcpyAsync(R.r_exon_end.data() + e0, o.exon_end, sizeof(int) * (size_t)ne, cudaMemcpyDeviceToHost, strm));
+				// device -> pinned staging -> result vectors
+				const size_t NT = (size_t)nt, NE = (size_t)ne;
+				const size_t oComp = 0, oSample = oComp + 4 * NT, oChr = oSample + 4 * NT, oGene = oChr + 4 * NT, oFpkm = (oGene + 4 * NT + 7) & ~(size_t)7,
+				             oCov = oFpkm + 8 * NT, oEo = oCov + 8 * NT, oEs = oEo + 8 * NT, oEe = oEs + 4 * NE, oStrand = oEe + 4 * NE, total = oStrand + NT;
+				if (!ub.stage.ensure(total + 64)) return ctx->fail("out of pinned host memory (result staging)");
+				char *hs = (char *)ub.stage.p;
+				CK(cudaMemcpyAsync(hs + oComp, o.comp, 4 * NT, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(hs + oSample, o.sample, 4 * NT, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(hs + oChr, o.chr, 4 * NT, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(hs + oGene, o.gene, 4 * NT, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(hs + oStrand, o.strand, NT, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(hs + oFpkm, o.fpkm, 8 * NT, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(hs + oCov, o.cov, 8 * NT, cudaMemcpyDeviceToHost, strm));
+				CK(cudaMemcpyAsync(hs + oEo, o.exon_off, 8 * NT, cudaMemcpyDeviceToHost, strm));
+				if (NE) {
+					CK(cudaMemcpyAsync(hs + oEs, o.exon_start, 4 * NE, cudaMemcpyDeviceToHost, strm));
+					CK(cudaMemcpyAsync(hs + oEe, o.exon_end, 4 * NE, cudaMemcpyDeviceToHost, strm));
+				}
 				CK(cudaStreamSynchronize(strm));
+				memcpy(R.r_comp.data() + t0, hs + oComp, 4 * NT);
+				memcpy(R.r_sample.data() + t0, hs + oSample, 4 * NT);
+				memcpy(R.r_chr.data() + t0, hs + oChr, 4 * NT);
+				memcpy(R.r_gene.data() + t0, hs + oGene, 4 * NT);
+				memcpy(R.r_strand.data() + t0, hs + oStrand, NT);
+				memcpy(R.r_fpkm.data() + t0, hs + oFpkm, 8 * NT);
+				memcpy(R.r_cov.data() + t0, hs + oCov, 8 * NT);
+				if (NE) {
+					memcpy(R.r_exon_start.data() + e0, hs + oEs, 4 * NE);
+					memcpy(R.r_exon_end.data() + e0, hs + oEe, 4 * NE);
+				}
+				const long long *eo = (const long long *)(hs + oEo);
 				lap("emit + copy back");
 				R.r_exon_off.pop_back();
+				R.r_exon_off.reserve(R.r_exon_off.size() + NT + 1);
 				for (long long k = 0; k < nt; ++k) R.r_exon_off.push_back((long long)e0 + eo[(size_t)k]);
 				R.r_exon_off.push_back((long long)e0 + ne);
 			}
@@ -878,8 +910,9 @@ int psc_solve(psc_ctx *ctx)
 		const cudaStream_t sHeavy = ctx->critSms > 0 ? ctx->sCrit : ctx->sMain;
 		if (dp_launch(heavy, sHeavy, st.db[0], counter, pdH, true) != 0) return 1;
 		if (dp_launch(rest, ctx->sSecond, st.db[1], counter + 8, pdR, false) != 0) return 1;
-		ResultSet resR;
+		ResultSet resR, resH;
 		resR.reset();
+		resH.reset();
 		int rcR = 0;
 		std::thread second([&]() {
 			cudaSetDevice(ctx->device);
@@ -896,20 +929,12 @@ int psc_solve(psc_ctx *ctx)
 			if (dp_finish(pdH, sHeavy, st.db[0], counter) != 0) return 1;
 			if (fetch_n_cand(heavy, sHeavy) != 0) return 1;
 			lap("heavy dp merge");
-			return run_units(2, sHeavy, st.ub[0], counter, st);
+			return run_units(2, sHeavy, st.ub[0], counter, resH);
 		}();
 		second.join();
 		if (rcH != 0 || rcR != 0) return 1;
 		lap("both chains done");
-		// pass 1 first, then pass 2, then one component-major list
-		ResultSet resH;
-		resH.reset();
-		std::swap(static_cast<ResultSet &>(st), resH);
-		st.reset();
-		st.append(resR);
-		const size_t pass1Tx = st.r_comp.size();
-		st.append(resH);
-		merge_passes(st, pass1Tx);
+		merge_passes(st, resR, resH);
 	} else {
 		if (!dpList.empty()) {
 			DpPending pd;

@@ -5,8 +5,10 @@
 struct UnitBufs {
 	DevBuf scr_off, scratch, pred_off, pred, n_pred, n_raw, n_exon, order, tx_off, ex_off, dbg;
 	DevBuf o_comp, o_sample, o_chr, o_gene, o_strand, o_exon_off, o_exon_start, o_exon_end, o_fpkm, o_cov;
+	HostBuf stage; // pinned staging of the results
 	void release()
 	{
+		stage.release();
 		DevBuf *all[] = {&scr_off, &scratch, &pred_off, &pred, &n_pred, &n_raw, &n_exon, &order, &tx_off, &ex_off, &dbg, &o_comp,
 		                 &o_sample, &o_chr, &o_gene, &o_strand, &o_exon_off, &o_exon_start, &o_exon_end, &o_fpkm, &o_cov};
 		for (DevBuf *b : all) b->release();
@@ -34,22 +36,6 @@ struct ResultSet {
 	{
 		r_comp.clear(); r_sample.clear(); r_chr.clear(); r_gene.clear(); r_strand.clear();
 		r_exon_off.assign(1, 0); r_exon_start.clear(); r_exon_end.clear(); r_fpkm.clear(); r_cov.clear();
-	}
-	// appends `o` behind this set
-	void append(const ResultSet &o)
-	{
-		const long long e0 = (long long)r_exon_start.size();
-		r_comp.insert(r_comp.end(), o.r_comp.begin(), o.r_comp.end());
-		r_sample.insert(r_sample.end(), o.r_sample.begin(), o.r_sample.end());
-		r_chr.insert(r_chr.end(), o.r_chr.begin(), o.r_chr.end());
-		r_gene.insert(r_gene.end(), o.r_gene.begin(), o.r_gene.end());
-		r_strand.insert(r_strand.end(), o.r_strand.begin(), o.r_strand.end());
-		r_fpkm.insert(r_fpkm.end(), o.r_fpkm.begin(), o.r_fpkm.end());
-		r_cov.insert(r_cov.end(), o.r_cov.begin(), o.r_cov.end());
-		r_exon_start.insert(r_exon_start.end(), o.r_exon_start.begin(), o.r_exon_start.end());
-		r_exon_end.insert(r_exon_end.end(), o.r_exon_end.begin(), o.r_exon_end.end());
-		r_exon_off.pop_back();
-		for (size_t k = 0; k < o.r_exon_off.size(); ++k) r_exon_off.push_back(e0 + o.r_exon_off[k]);
 	}
 };
 

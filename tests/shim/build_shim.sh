@@ -13,5 +13,5 @@ g++ -std=c++17 -O2 -g -Wall -o tests/shim/_build/psc_check_shim tools/psc_check.
 # the `classes` front end linked against the shim, so the host logic (argv, BAM decode, sharding,
 # Q8, GTF writer) can be diffed against the reference's GTFs without a GPU
 g++ -std=c++17 -O2 -g -Wall -o tests/shim/_build/classes_shim psiclass_b200/csrc/host/classes_main.cpp \
-    psiclass_b200/csrc/host/bam_io.cpp psiclass_b200/csrc/host/subexon_graph.cpp psiclass_b200/csrc/host/gtf_out.cpp \
+    psiclass_b200/csrc/host/bam_io.cpp psiclass_b200/csrc/host/subexon_graph.cpp psiclass_b200/csrc/host/gtf_out.cpp psiclass_b200/csrc/host/vote.cpp \
     -Ltests/shim/_build -lpsc_shim -Wl,-rpath,'$ORIGIN' -lz -lpthread
