@@ -380,7 +380,7 @@ def main():
 
     if rank == 0:
         names = ["group_ranges", "build_constraints", "prologue", "enumerate", "dp_units", "units_pick1", "emit", "dp_merge",
-                 "units_pick2_refine_em", "units_rescue", "dp_program", "-"]
+                 "units_pick2_refine_em", "units_rescue", "dp_program", "dp_program_thread_per_unit"]
         dom = max(range(12), key=lambda k: kms[k])
         peak, peak_src = measured_peak()
         per_launch_ms = kms[dom] / max(1, kcnt[dom])

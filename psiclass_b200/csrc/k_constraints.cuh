@@ -141,8 +141,87 @@ PSC_DEV uint64_t mix64(uint64_t z)
 
 // --------------------------------------------------------------------------------------------
 // K1+K2 fused: one cooperative group builds the whole table of group (sample, comp).
+//
+// Equal bit vectors are found by HASHING (open addressing over the candidates' bit rows), so only the distinct
+// constraints -- typically a tenth of the reads -- are sorted; the mate join is a hash join on the read-name key and
+// the mate-pair list is deduplicated the same way.  Tables and the lists that get sorted live in the group's slice of
+// shared memory when they fit (PSC_CG_H slots / PSC_CG_D entries), else in the group's own per-read scratch rows.
 // --------------------------------------------------------------------------------------------
-PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, int c, bool primaryAsUnique)
+#define PSC_CG_H 512
+#define PSC_CG_D 256
+#define PSC_CG_SMEM_INTS (PSC_CG_H + PSC_CG_D)
+
+PSC_DEV uint32_t hash_words(const uint64_t *b, int W)
+{
+	uint64_t h = 0x9E3779B97F4A7C15ull;
+	for (int w = 0; w < W; ++w) {
+		h ^= b[w] + (uint64_t)w;
+		h *= 0xff51afd7ed558ccdull;
+		h ^= h >> 29;
+	}
+	return (uint32_t)(h ^ (h >> 32));
+}
+
+// number of slots for up to `items` entries in a group of R reads: a power of two > items, never more than 2R
+PSC_DEV int table_slots(int items)
+{
+	int H = 16;
+	while (H < 2 * items) H <<= 1;
+	return H;
+}
+
+// A group with NH = 3 reads: the weight sums are inexact, so they are accumulated in the order the reference's
+// std::sort leaves equal constraints in, including its capacity-triggered partial coalescing
+// (Constraints.cpp:378-390; the vector starts empty per component, :247-254, so capacities are 1, 2, 4, ...).
+// comp(a, b) of CompSortConstraints is cid[a] < cid[b] once the rows are numbered in sorted order.
+PSC_DEV void nh3_weights(const Coop &co, const SampleDev &s, int lo, int R)
+{
+	if (co.lane == 0) {
+		const int4 *meta = s.cand_meta + lo;
+		int *P = s.sortbuf + 4 * (long long)lo, *tk = P + R, *ek = s.pair_uniq_in + lo;
+		double *ew = s.con_weight + lo, *tw = (double *)(s.pair_key + lo);
+		int size = 0, cap = 0, thr = 16384;
+		auto coalesce = [&]() {
+			if (size <= 0) return;
+			for (int i = 0; i < size; ++i) P[i] = i;
+			std_sort_order(P, size, [&](int x, int y) { return ek[x] < ek[y]; });
+			int k = 0;
+			tk[0] = ek[P[0]];
+			tw[0] = ew[P[0]];
+			for (int i = 1; i < size; ++i) {
+				int x = P[i];
+				if (ek[x] == tk[k]) tw[k] += ew[x];
+				else {
+					++k;
+					tk[k] = ek[x];
+					tw[k] = ew[x];
+				}
+			}
+			size = k + 1;
+			for (int i = 0; i < size; ++i) {
+				ek[i] = tk[i];
+				ew[i] = tw[i];
+			}
+		};
+		for (int r = 0; r < R; ++r) {
+			int4 mt = meta[r];
+			if (mt.x < 0) continue;
+			if (size == cap) cap = cap ? 2 * cap : 1;
+			int nh = mt.w & 0xff;
+			ek[size] = s.cand_cid[lo + r];
+			ew[size] = (1.0 / (double)(nh > 0 ? nh : 1)) * 10; // Constraints.cpp:294-296 with Q1
+			++size;
+			if (size > thr && size == cap) {
+				coalesce();
+				if (size >= cap / 2) thr *= 2;
+			}
+		}
+		coalesce(); // ek[k] == k and ew[k] == con_weight[lo + k] from here on
+	}
+	co.sync();
+}
+
+PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, int c, bool primaryAsUnique, int *smem)
 {
 	int lo = s.grp_lo[c], hi = s.grp_hi[c];
 	int R = hi - lo;
@@ -154,128 +233,109 @@ PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, 
 	}
 	uint64_t *cbits = s.cand_bits + s.bits_off[c];
 	uint64_t *obits = s.con_bits + s.bits_off[c];
-	int *idx = s.sortbuf + 2 * (long long)lo;
+	// global scratch rows of the group: gA 4R ints (hash tables), gB 2R ints (the pair-key row, free until the mate
+	// join), gC R ints
+	int *gA = s.sortbuf + 4 * (long long)lo;
+	int *gB = (int *)(s.pair_key + lo);
+	int *gC = s.pair_uniq_in + lo;
+	int *smTable = smem, *smList = smem ? smem + PSC_CG_H : nullptr;
+	const int4 *meta = s.cand_meta + lo;
 
-	// ---- A: convert every read; compact the accepted ones ----
+	// ---- A: convert every read ----
 	int V = 0;
 	for (int b0 = 0; b0 < R; b0 += co.n) {
 		int r = b0 + co.lane;
 		bool ok = false;
 		if (r < R) {
-			int4 meta;
-			ok = convert_read(g, s, c, lo + r, primaryAsUnique, cbits + (long long)r * W, W, meta) >= 0;
-			s.cand_meta[lo + r] = meta;
+			int4 mt;
+			ok = convert_read(g, s, c, lo + r, primaryAsUnique, cbits + (long long)r * W, W, mt) >= 0;
+			s.cand_meta[lo + r] = mt;
 			s.cand_cid[lo + r] = -1;
 		}
-		uint32_t m = co.ballot(ok);
-		if (ok) idx[V + co.rank_in(m)] = r;
-		V += popc32(m);
+		V += popc32(co.ballot(ok));
 	}
 	co.sync();
 	if (V == 0) {
 		if (co.lane == 0) { s.n_con[c] = 0; s.n_pair[c] = 0; }
 		return;
 	}
-	// ---- B: sort by (first, bit-lexicographic) == CompSortConstraints ----
-	const int4 *meta = s.cand_meta + lo;
-	coop_sort(co, idx, V, [&](int a, int b) {
-		int fa = meta[a].x, fb = meta[b].x;
-		if (fa != fb) return fa < fb;
-		return cmp_bits_without_first(cbits + (long long)a * W, cbits + (long long)b * W, W) < 0;
-	});
-	// ---- C: run-length merge -> constraint rows ----
-	for (int r = co.lane; r < V; r += co.n) {
-		s.con_support[lo + r] = 0;
-		s.con_uniq[lo + r] = 0;
-		s.con_maxlen[lo + r] = 0;
-		s.con_nhcnt[lo + r] = make_int4(0, 0, 0, 0);
+	// ---- B: equal vectors share a slot of a hash table over the bit rows; the slot keeps one representative read ----
+	int H = table_slots(V); // < 4V <= 4R
+	int *table = (smTable && H <= PSC_CG_H) ? smTable : gA;
+	for (int k = co.lane; k < H; k += co.n) table[k] = -1;
+	co.sync();
+	for (int b0 = 0; b0 < R; b0 += co.n) {
+		int r = b0 + co.lane;
+		if (r < R && meta[r].x >= 0) {
+			const uint64_t *mb = cbits + (long long)r * W;
+			uint32_t h = hash_words(mb, W) & (uint32_t)(H - 1);
+			for (;;) {
+				int old = atomic_cas(&table[h], -1, r);
+				if (old == -1) break; // r represents this vector
+				const uint64_t *ob = cbits + (long long)old * W;
+				bool same = true;
+				for (int w = 0; w < W; ++w) same = same && ob[w] == mb[w];
+				if (same) break;
+				h = (h + 1) & (uint32_t)(H - 1); // the table is at most half full
+			}
+			s.cand_cid[lo + r] = (int)h;
+		}
 	}
 	co.sync();
+	// ---- C: the distinct vectors, sorted == CompSortConstraints, are the constraint rows ----
 	int C = 0;
+	{
+		int *dlist = gB; // room for 2R >= next_pow2(C) entries
+		for (int k0 = 0; k0 < H; k0 += co.n) {
+			int k = k0 + co.lane;
+			bool occ = k < H && table[k] >= 0;
+			uint32_t m = co.ballot(occ);
+			if (occ) dlist[C + co.rank_in(m)] = k;
+			C += popc32(m);
+		}
+		co.sync();
+		if (smList && next_pow2(C) <= PSC_CG_D) {
+			for (int k = co.lane; k < C; k += co.n) smList[k] = dlist[k];
+			dlist = smList;
+			co.sync();
+		}
+		coop_sort(co, dlist, C, [&](int a, int b) {
+			int ra = table[a], rb = table[b];
+			int fa = meta[ra].x, fb = meta[rb].x;
+			if (fa != fb) return fa < fb;
+			return cmp_bits_without_first(cbits + (long long)ra * W, cbits + (long long)rb * W, W) < 0;
+		});
+		for (int k = co.lane; k < C; k += co.n) {
+			int rep = table[dlist[k]];
+			for (int w = 0; w < W; ++w) obits[(long long)k * W + w] = cbits[(long long)rep * W + w];
+			s.con_first[lo + k] = meta[rep].x;
+			s.con_last[lo + k] = meta[rep].y;
+			s.con_support[lo + k] = 0;
+			s.con_uniq[lo + k] = 0;
+			s.con_maxlen[lo + k] = 0;
+			s.con_nhcnt[lo + k] = make_int4(0, 0, 0, 0);
+		}
+		co.sync();
+		for (int k = co.lane; k < C; k += co.n) table[dlist[k]] = k; // slot -> row
+		co.sync();
+	}
 	bool has3 = false;
-	for (int b0 = 0; b0 < V; b0 += co.n) {
-		int p = b0 + co.lane;
-		bool head = false;
-		int me = -1;
-		if (p < V) {
-			me = idx[p];
-			if (p == 0) head = true;
-			else {
-				int pv = idx[p - 1];
-				head = meta[me].x != meta[pv].x ||
-				       cmp_bits_without_first(cbits + (long long)me * W, cbits + (long long)pv * W, W) != 0;
-			}
-		}
-		uint32_t m = co.ballot(head);
-		if (p < V) {
-			int cid = C + popc32(m & ((2u << co.lane) - 1u)) - 1;
-			s.cand_cid[lo + me] = cid;
-			int4 mt = meta[me];
-			if (head) {
-				for (int w = 0; w < W; ++w) obits[(long long)cid * W + w] = cbits[(long long)me * W + w];
-				s.con_first[lo + cid] = mt.x;
-				s.con_last[lo + cid] = mt.y;
-			}
-			atomic_add(&s.con_support[lo + cid], 1);
-			atomic_add(&s.con_uniq[lo + cid], (mt.w >> 8) & 1);
-			atomic_max(&s.con_maxlen[lo + cid], mt.z);
-			int nh = mt.w & 0xff;
-			int *cnt = (int *)&s.con_nhcnt[lo + cid];
-			if (nh >= 1 && nh <= 4) atomic_add(&cnt[nh - 1], 1);
-			has3 = has3 || nh == 3;
-		}
-		C += popc32(m);
+	for (int r = co.lane; r < R; r += co.n) {
+		int4 mt = meta[r];
+		if (mt.x < 0) continue;
+		int cid = table[s.cand_cid[lo + r]];
+		s.cand_cid[lo + r] = cid;
+		atomic_add(&s.con_support[lo + cid], 1);
+		atomic_add(&s.con_uniq[lo + cid], (mt.w >> 8) & 1);
+		atomic_max(&s.con_maxlen[lo + cid], mt.z);
+		int nh = mt.w & 0xff;
+		int *cnt = (int *)&s.con_nhcnt[lo + cid];
+		if (nh >= 1 && nh <= 4) atomic_add(&cnt[nh - 1], 1);
+		has3 = has3 || nh == 3;
 	}
 	has3 = co.any(has3);
 	co.sync();
-	// ---- C2: a group with NH = 3 reads: the weight sums are inexact, so they are accumulated in the order the
-	// reference's std::sort leaves equal constraints in, including its capacity-triggered partial coalescing
-	// (Constraints.cpp:378-390; the vector starts empty per component, :247-254, so capacities are 1, 2, 4, ...).
-	// comp(a, b) of CompSortConstraints is cid[a] < cid[b] now that the rows are numbered in sorted order.
-	if (has3) {
-		if (co.lane == 0) {
-			int *P = idx, *tk = idx + R, *ek = s.pair_uniq_in + lo;
-			double *ew = s.con_weight + lo, *tw = (double *)(s.pair_key + lo);
-			int size = 0, cap = 0, thr = 16384;
-			auto coalesce = [&]() {
-				if (size <= 0) return;
-				for (int i = 0; i < size; ++i) P[i] = i;
-				std_sort_order(P, size, [&](int x, int y) { return ek[x] < ek[y]; });
-				int k = 0;
-				tk[0] = ek[P[0]];
-				tw[0] = ew[P[0]];
-				for (int i = 1; i < size; ++i) {
-					int x = P[i];
-					if (ek[x] == tk[k]) tw[k] += ew[x];
-					else {
-						++k;
-						tk[k] = ek[x];
-						tw[k] = ew[x];
-					}
-				}
-				size = k + 1;
-				for (int i = 0; i < size; ++i) {
-					ek[i] = tk[i];
-					ew[i] = tw[i];
-				}
-			};
-			for (int r = 0; r < R; ++r) {
-				int4 mt = meta[r];
-				if (mt.x < 0) continue;
-				if (size == cap) cap = cap ? 2 * cap : 1;
-				int nh = mt.w & 0xff;
-				ek[size] = s.cand_cid[lo + r];
-				ew[size] = (1.0 / (double)(nh > 0 ? nh : 1)) * 10; // Constraints.cpp:294-296 with Q1
-				++size;
-				if (size > thr && size == cap) {
-					coalesce();
-					if (size >= cap / 2) thr *= 2;
-				}
-			}
-			coalesce(); // ek[k] == k and ew[k] == con_weight[lo + k] from here on
-		}
-		co.sync();
-	}
+	if (has3) nh3_weights(co, s, lo, R);
 	// ---- D: mate pairs ----
 	int M = 0;
 	if (s.frag_stdev == 0) {
@@ -289,45 +349,61 @@ PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, 
 		}
 		M = C;
 	} else {
-		// join list: accepted reads that are a left or a right mate
+		// MateReadIds keys an entry by (read id, matePos); the right mate asks with its own pos.  Hash join: the left
+		// mates go into a table keyed by name_key ^ mix(matePos), the latest read winning a key (the reference's heap
+		// hands out the last inserted entry); every right mate looks its key up.
+		uint64_t *jkey = s.pair_key + lo;
 		int J = 0;
 		for (int b0 = 0; b0 < R; b0 += co.n) {
 			int r = b0 + co.lane;
 			int kind = 0;
 			if (r < R && meta[r].x >= 0) kind = (meta[r].w >> 16) & 3;
-			bool in = kind == 1 || kind == 2;
-			uint32_t m = co.ballot(in);
-			if (in) {
-				idx[J + co.rank_in(m)] = r;
-				// MateReadIds keys an entry by (read id, matePos); the right mate asks with its own pos
+			if (kind == 1 || kind == 2) {
 				int jp = kind == 1 ? s.mate_pos[lo + r] : s.pos[lo + r];
-				s.pair_key[lo + r] = s.name_key[lo + r] ^ mix64((uint64_t)(uint32_t)jp + 0x9e3779b97f4a7c15ull);
+				jkey[r] = s.name_key[lo + r] ^ mix64((uint64_t)(uint32_t)jp + 0x9e3779b97f4a7c15ull);
 			}
-			J += popc32(m);
+			J += popc32(co.ballot(kind == 1));
+		}
+		H = table_slots(J);
+		table = (smTable && H <= PSC_CG_H) ? smTable : gA;
+		for (int k = co.lane; k < H; k += co.n) table[k] = -1;
+		co.sync();
+		for (int r = co.lane; r < R; r += co.n) {
+			if (meta[r].x < 0 || ((meta[r].w >> 16) & 3) != 1) continue;
+			const uint64_t key = jkey[r];
+			uint32_t h = (uint32_t)mix64(key) & (uint32_t)(H - 1);
+			for (;;) {
+				int old = atomic_cas(&table[h], -1, r);
+				if (old == -1) break;
+				if (jkey[old] == key) { // same key: the later read wins (whoever sits in the slot has this key)
+					atomic_max(&table[h], r);
+					break;
+				}
+				h = (h + 1) & (uint32_t)(H - 1);
+			}
 		}
 		co.sync();
-		const uint64_t *jkey = s.pair_key + lo;
-		coop_sort(co, idx, J, [&](int a, int b) {
-			uint64_t ka = jkey[a], kb = jkey[b];
-			if (ka != kb) return ka < kb;
-			int ra = (meta[a].w >> 16) & 3, rb = (meta[b].w >> 16) & 3;
-			if (ra != rb) return ra < rb; // left mates (1) before right mates (2)
-			return a < b;
-		});
-		// every right mate looks back for the last left mate with its key (later insertions win)
-		// matches are recorded in cand_cid's sibling array pair_uniq_in as (left read) or -1
-		for (int p = co.lane; p < J; p += co.n) {
-			int me = idx[p];
+		// right mates: matched left read, or -1
+		for (int r = co.lane; r < R; r += co.n) {
 			int left = -1;
-			if (((meta[me].w >> 16) & 3) == 2) {
-				int q = p - 1;
-				while (q >= 0 && jkey[idx[q]] == jkey[me] && ((meta[idx[q]].w >> 16) & 3) == 2) --q;
-				if (q >= 0 && jkey[idx[q]] == jkey[me]) left = idx[q];
+			if (meta[r].x >= 0 && ((meta[r].w >> 16) & 3) == 2) {
+				const uint64_t key = jkey[r];
+				uint32_t h = (uint32_t)mix64(key) & (uint32_t)(H - 1);
+				for (;;) {
+					int cur = table[h];
+					if (cur < 0) break;
+					if (jkey[cur] == key) {
+						left = cur;
+						break;
+					}
+					h = (h + 1) & (uint32_t)(H - 1);
+				}
 			}
-			s.pair_uniq_in[lo + me] = left;
+			gC[r] = left;
 		}
 		co.sync();
-		// pair list: (cid[left], cid[me]) for matched right mates, (cid, cid) for same-position first mates
+		// pair list: (cid[left], cid[me]) for matched right mates, (cid, cid) for same-position first mates.  The pair
+		// keys replace the join keys (all look-ups are done), then equal pairs share a slot like equal vectors did.
 		int Pn = 0;
 		for (int b0 = 0; b0 < R; b0 += co.n) {
 			int r = b0 + co.lane;
@@ -337,7 +413,7 @@ PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, 
 				int kind = (meta[r].w >> 16) & 3;
 				int cj = s.cand_cid[lo + r];
 				if (kind == 2) {
-					int left = s.pair_uniq_in[lo + r];
+					int left = gC[r];
 					if (left >= 0) {
 						in = true;
 						key = ((uint64_t)(uint32_t)s.cand_cid[lo + left] << 32) | (uint32_t)cj;
@@ -347,45 +423,63 @@ PSC_DEV void build_group(const Coop &co, const GraphDev &g, const SampleDev &s, 
 					key = ((uint64_t)(uint32_t)cj << 32) | (uint32_t)cj;
 				}
 			}
-			uint32_t m = co.ballot(in);
-			if (in) idx[Pn + co.rank_in(m)] = r;
-			Pn += popc32(m);
-			// keys are written after the left-read lookups of this chunk are done
+			if (r < R) {
+				jkey[r] = key;
+				gC[r] = in ? 1 : 0;
+			}
+			Pn += popc32(co.ballot(in));
+		}
+		co.sync();
+		if (Pn > 0) {
+			const uint64_t *pkey = jkey;
+			H = table_slots(Pn); // < 4 Pn <= 4R
+			table = (smTable && H <= PSC_CG_H) ? smTable : gA;
+			for (int k = co.lane; k < H; k += co.n) table[k] = -1;
 			co.sync();
-			if (in) s.pair_key[lo + r] = key;
-		}
-		co.sync();
-		const uint64_t *pkey = s.pair_key + lo;
-		coop_sort(co, idx, Pn, [&](int a, int b) {
-			uint64_t ka = pkey[a], kb = pkey[b];
-			if (ka != kb) return ka < kb;
-			return a < b;
-		});
-		for (int r = co.lane; r < Pn; r += co.n) {
-			s.pair_support[lo + r] = 0;
-			s.pair_uniq[lo + r] = 0;
-		}
-		co.sync();
-		for (int b0 = 0; b0 < Pn; b0 += co.n) {
-			int p = b0 + co.lane;
-			bool head = false;
-			int me = -1;
-			if (p < Pn) {
-				me = idx[p];
-				head = p == 0 || pkey[me] != pkey[idx[p - 1]];
-			}
-			uint32_t m = co.ballot(head);
-			if (p < Pn) {
-				int pid = M + popc32(m & ((2u << co.lane) - 1u)) - 1;
-				if (head) {
-					s.pair_i[lo + pid] = (int)(pkey[me] >> 32);
-					s.pair_j[lo + pid] = (int)(pkey[me] & 0xffffffffu);
-					s.pair_ec[lo + pid] = 2;
+			for (int r = co.lane; r < R; r += co.n) {
+				if (!gC[r]) continue;
+				const uint64_t key = pkey[r];
+				uint32_t h = (uint32_t)mix64(key) & (uint32_t)(H - 1);
+				for (;;) {
+					int old = atomic_cas(&table[h], -1, r);
+					if (old == -1 || pkey[old] == key) break;
+					h = (h + 1) & (uint32_t)(H - 1);
 				}
-				atomic_add(&s.pair_support[lo + pid], 1);
-				atomic_add(&s.pair_uniq[lo + pid], (meta[me].w >> 8) & 1);
+				gC[r] = (int)h + 1; // slot of the pair read
 			}
-			M += popc32(m);
+			co.sync();
+			int *dlist = (int *)(s.con_norm + lo); // 2R ints, written by step E only
+			for (int k0 = 0; k0 < H; k0 += co.n) {
+				int k = k0 + co.lane;
+				bool occ = k < H && table[k] >= 0;
+				uint32_t m = co.ballot(occ);
+				if (occ) dlist[M + co.rank_in(m)] = k;
+				M += popc32(m);
+			}
+			co.sync();
+			if (smList && next_pow2(M) <= PSC_CG_D) {
+				for (int k = co.lane; k < M; k += co.n) smList[k] = dlist[k];
+				dlist = smList;
+				co.sync();
+			}
+			coop_sort(co, dlist, M, [&](int a, int b) { return pkey[table[a]] < pkey[table[b]]; });
+			for (int k = co.lane; k < M; k += co.n) {
+				uint64_t key = pkey[table[dlist[k]]];
+				s.pair_i[lo + k] = (int)(key >> 32);
+				s.pair_j[lo + k] = (int)(key & 0xffffffffu);
+				s.pair_ec[lo + k] = 2;
+				s.pair_support[lo + k] = 0;
+				s.pair_uniq[lo + k] = 0;
+			}
+			co.sync();
+			for (int k = co.lane; k < M; k += co.n) table[dlist[k]] = k; // slot -> pair row
+			co.sync();
+			for (int r = co.lane; r < R; r += co.n) {
+				if (!gC[r]) continue;
+				int pid = table[gC[r] - 1];
+				atomic_add(&s.pair_support[lo + pid], 1);
+				atomic_add(&s.pair_uniq[lo + pid], (meta[r].w >> 8) & 1);
+			}
 		}
 	}
 	co.sync();

@@ -58,6 +58,9 @@ struct DpScratch {
 	// second candidate buffer for the permutation step of CoalesceSameTranscripts
 	uint64_t *c2b;
 	int *c2f, *c2l;
+	// shared-memory sort buffer of the merge kernel (null: sort indices in global memory)
+	uint64_t *sort64;
+	int sort64Cap;
 };
 
 // frame memory of the walk: 5 ints per path position, 10 per owner (k_dp_walk.cuh)
@@ -115,6 +118,8 @@ __host__ __device__ inline size_t dp_scratch_layout(DpScratch *o, char *base, in
 	s.c2b = cv.take<uint64_t>((size_t)candCap * W + 1);
 	s.c2f = cv.take<int>((size_t)candCap + 1);
 	s.c2l = cv.take<int>((size_t)candCap + 1);
+	s.sort64 = nullptr;
+	s.sort64Cap = 0;
 	if (o) *o = s;
 	return (cv.off + 15) & ~(size_t)15;
 }
@@ -753,6 +758,32 @@ PSC_DEV int dp_coalesce(DpState &st, uint64_t *cb, int *cf, int *cl, int A)
 	DpScratch &d = st.d;
 	int W = st.W;
 	if (A <= 1) return A;
+	if (d.sort64 && next_pow2(A) <= d.sort64Cap && st.v.n < 4096 && A <= 4096) {
+		// sort (52-bit prefix | 12-bit row index) words in shared memory: the prefix is `first` and the 40 subexons
+		// after it, complemented so that the row WITH the earlier bit comes first (CompSortTranscripts); only rows
+		// with equal prefixes are compared in full
+		for (int i = co.lane; i < A; i += co.n) {
+			const uint64_t *r = cb + (long long)i * W;
+			int f = cf[i];
+			uint64_t next40 = 0; // bits f+1 .. f+40, the earliest subexon in the top position
+			for (int q = 0; q < 40; ++q) {
+				int b = f + 1 + q;
+				next40 = (next40 << 1) | (uint64_t)((b < st.v.n && bt_test(r, b)) ? 0 : 1);
+			}
+			d.sort64[i] = ((uint64_t)f << 52) | (next40 << 12) | (uint64_t)i;
+		}
+		co.sync();
+		coop_sort64(co, d.sort64, A, [&](uint64_t x, uint64_t y) {
+			if ((x >> 12) != (y >> 12)) return x < y;
+			int a = (int)(x & 4095), b = (int)(y & 4095);
+			const uint64_t *ra = cb + (long long)a * W, *rb = cb + (long long)b * W;
+			for (int w = 0; w < W; ++w)
+				if (ra[w] != rb[w]) return brev64(ra[w]) > brev64(rb[w]);
+			return a < b;
+		});
+		for (int i = co.lane; i < A; i += co.n) d.sortidx[i] = (int)(d.sort64[i] & 4095);
+		co.sync();
+	} else {
 	for (int i = co.lane; i < A; i += co.n) d.sortidx[i] = i;
 	co.sync();
 	coop_sort(co, d.sortidx, A, [&](int a, int b) {
@@ -763,6 +794,7 @@ PSC_DEV int dp_coalesce(DpState &st, uint64_t *cb, int *cf, int *cl, int A)
 			if (ra[w] != rb[w]) return brev64(ra[w]) > brev64(rb[w]); // CompSortTranscripts, see tx_row_less
 		return a < b; // equal rows: keep the order of arrival
 	});
+	}
 	// unique rows -> second buffer, then back
 	int K = 0;
 	for (int b0 = 0; b0 < A; b0 += co.n) {
@@ -1085,7 +1117,7 @@ __host__ __device__ inline size_t dp_merge_layout(DpMergeScratch *o, char *base,
 
 // units of component c are u0 .. u0+S-1, already in the reference's visiting order
 PSC_DEVN void dp_merge(const Coop &co, const GraphDev &g, const SolveDev &sv, int c, const DpUnit *units, int u0,
-                       const int *n_tx, const char *txBase, char *scratch)
+                       const int *n_tx, const char *txBase, char *scratch, uint64_t *sort64, int sort64Cap)
 {
 	DpState st;
 	st.co = co;
@@ -1100,6 +1132,8 @@ PSC_DEVN void dp_merge(const Coop &co, const GraphDev &g, const SolveDev &sv, in
 	st.d.c2b = ms.c2b;
 	st.d.c2f = ms.c2f;
 	st.d.c2l = ms.c2l;
+	st.d.sort64 = sort64;
+	st.d.sort64Cap = sort64Cap;
 	st.cs = sv.can_start + v.base;
 	st.ce = sv.can_end + v.base;
 	st.W = W;

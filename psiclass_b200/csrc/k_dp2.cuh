@@ -112,14 +112,14 @@ __host__ __device__ inline size_t dp2_smem_wanted(int n)
 // nullptr (then the hot part follows the cold part in the arena).  With cold == nullptr and coldBytes == 0 returns the
 // arena bytes a unit needs for dp2_wanted_keys(n) keys with everything in global memory.
 __host__ __device__ inline size_t dp2_layout(DpScratch *od, Dp2 *oz, char *cold, size_t coldBytes, char *hot, size_t hotBytes, int n,
-                                             int E, int Cmax)
+                                             int E, int Cmax, int keysForSizing = 0)
 {
 	Carver cv(cold);
 	int W = (n + 63) >> 6;
 	DpScratch s;
 	s.ent = nullptr; s.eepoch = nullptr; s.ebits = nullptr; s.f2Base = 0; s.hashBase = 0; s.hashMax = 0;
 	s.P = nullptr; s.fr = nullptr; s.fdcover = nullptr; s.fdbeta = nullptr; s.fdkey = nullptr; s.pbits = nullptr;
-	s.fdmeta = nullptr; s.fdbits = nullptr; s.sortidx = nullptr; s.c2b = nullptr; s.c2f = nullptr; s.c2l = nullptr;
+	s.fdmeta = nullptr; s.fdbits = nullptr; s.sortidx = nullptr; s.c2b = nullptr; s.c2f = nullptr; s.c2l = nullptr; s.sort64 = nullptr; s.sort64Cap = 0;
 	s.txb = nullptr; s.txf = nullptr; s.txl = nullptr; s.txCap = 0;
 	s.tcb = cv.take<uint64_t>((size_t)Cmax * W + 1);
 	s.tcf = cv.take<int>((size_t)Cmax + 1);
@@ -151,7 +151,7 @@ __host__ __device__ inline size_t dp2_layout(DpScratch *od, Dp2 *oz, char *cold,
 	const size_t hotFixed = dp2_hot_fixed(n, W);
 	const bool split = hot != nullptr;
 	const int frPerKey = split ? DP2_FR_PER_KEY_SMEM : DP2_FR_PER_KEY_GLOBAL;
-	long long K = dp2_wanted_keys(n), L;
+	long long K = keysForSizing > 0 ? keysForSizing : dp2_wanted_keys(n), L;
 	if (coldBytes > 0) {
 		if (split) {
 			K = hotBytes > hotFixed + 64 ? (long long)((hotBytes - hotFixed - 64) / dp2_hot_per_key(W, frPerKey)) : 0;
@@ -707,6 +707,7 @@ template <int NW> PSC_DEVN int dp3_solve_root(DpState &stRef, int start)
 	double o_cover = -1, o_beta = 1e300;
 	int o_plast = 0, o_pstrand = 0;
 	uint64_t ob[NW];
+	for (int w = 0; w < NW; ++w) ob[w] = 0;
 	int rk = z.key1[start], rs = 0, ret = -1;
 call : {
 	Dp2Key *k = keys + rk;

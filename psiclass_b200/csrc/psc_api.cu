@@ -59,6 +59,15 @@ __global__ void __launch_bounds__(128) k_build_constraints(GraphDev g, const Sam
                                                           int primaryAsUnique, int width)
 {
 	Coop co = make_coop(width);
+	// hash tables / sort lists of a group: a slice of shared memory per warp; the serial CPU harness uses a plain array
+	int *smem = nullptr;
+#ifndef PSC_CPU_SHIM
+	__shared__ int cg_smem[4 * PSC_CG_SMEM_INTS];
+	if (width == 32) smem = cg_smem + (threadIdx.x >> 5) * PSC_CG_SMEM_INTS;
+#else
+	static thread_local int cg_host[PSC_CG_SMEM_INTS];
+	smem = cg_host;
+#endif
 	for (;;) {
 		int u = 0;
 		if (co.lane == 0) u = atomic_add(counter, 1);
@@ -66,7 +75,7 @@ __global__ void __launch_bounds__(128) k_build_constraints(GraphDev g, const Sam
 		if (u >= nUnits) break;
 		int unit = order ? order[u] : u;
 		int smp = unit / g.n_comp, c = unit % g.n_comp;
-		build_group(co, g, samples[smp], c, primaryAsUnique != 0);
+		build_group(co, g, samples[smp], c, primaryAsUnique != 0, smem);
 		co.sync();
 	}
 }
@@ -161,8 +170,8 @@ struct psc_ctx {
 	// few critical (component, sample) units whose single-warp latency chains set the step time (they then run one
 	// warp per SM sub-partition, undisturbed) and the rest for everything else: sMain / sSecond live in the big
 	// partition, sCrit in the small one.  Otherwise these are ordinary streams (sMain == stream, sSecond == stream2).
-	cudaStream_t sMain = 0, sSecond = 0, sCrit = 0;
-	cudaEvent_t evCritGo = 0, evCritDone = 0;
+	cudaStream_t sMain = 0, sSecond = 0, sCrit = 0, sThird = 0; // sThird: the one-thread-per-unit DP launch of the bulk
+	cudaEvent_t evCritGo = 0, evCritDone = 0, evT1Go = 0, evT1Done = 0;
 	int critSms = 0; // SMs of the critical partition, 0: no partitioning
 #ifndef PSC_CPU_SHIM
 	CUgreenCtx gctxCrit = nullptr, gctxRest = nullptr;
@@ -289,6 +298,8 @@ int psc_create(psc_ctx **out, int device)
 	memset(&ctx->prm, 0, sizeof(ctx->prm));
 	cudaEventCreateWithFlags(&ctx->evCritGo, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&ctx->evCritDone, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->evT1Go, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->evT1Done, cudaEventDisableTiming);
 	ctx->sMain = ctx->stream;
 	ctx->sSecond = ctx->stream2;
 #ifndef PSC_CPU_SHIM
@@ -320,7 +331,7 @@ int psc_create(psc_ctx **out, int device)
 			CUdevResource all, crit, rest;
 			unsigned int groups = 1;
 			CUdevResourceDesc dCrit = nullptr, dRest = nullptr;
-			CUstream a = nullptr, b = nullptr, c = nullptr;
+			CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr;
 			ok = ok && devGet(&dev, device) == CUDA_SUCCESS && getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
 			     split(&crit, &groups, &all, &rest, 0, (unsigned int)want) == CUDA_SUCCESS && groups == 1 && rest.sm.smCount > 0 &&
 			     mkDesc(&dCrit, &crit, 1) == CUDA_SUCCESS && mkDesc(&dRest, &rest, 1) == CUDA_SUCCESS &&
@@ -328,11 +339,13 @@ int psc_create(psc_ctx **out, int device)
 			     mkCtx(&ctx->gctxRest, dRest, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
 			     mkStream(&a, ctx->gctxRest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS &&
 			     mkStream(&b, ctx->gctxRest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS &&
-			     mkStream(&c, ctx->gctxCrit, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+			     mkStream(&c, ctx->gctxCrit, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS &&
+			     mkStream(&d, ctx->gctxRest, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
 			if (ok) {
 				ctx->sMain = (cudaStream_t)a;
 				ctx->sSecond = (cudaStream_t)b;
 				ctx->sCrit = (cudaStream_t)c;
+				ctx->sThird = (cudaStream_t)d;
 				ctx->critSms = (int)crit.sm.smCount;
 				if (getenv("PSC_DEBUG_HOST"))
 					fprintf(stderr, "[host] SM partitions: %u critical + %u\n", crit.sm.smCount, rest.sm.smCount);
@@ -341,7 +354,7 @@ int psc_create(psc_ctx **out, int device)
 		}
 	}
 #endif
-	if (!ctx->sCrit && cudaStreamCreate(&ctx->sCrit) != cudaSuccess) {
+	if ((!ctx->sCrit && cudaStreamCreate(&ctx->sCrit) != cudaSuccess) || (!ctx->sThird && cudaStreamCreate(&ctx->sThird) != cudaSuccess)) {
 		delete ctx;
 		return 5;
 	}
@@ -368,6 +381,9 @@ void psc_destroy(psc_ctx *ctx)
 	cudaEventDestroy(ctx->evCritGo);
 	cudaEventDestroy(ctx->evCritDone);
 	cudaStreamDestroy(ctx->sCrit);
+	cudaStreamDestroy(ctx->sThird);
+	cudaEventDestroy(ctx->evT1Go);
+	cudaEventDestroy(ctx->evT1Done);
 	if (ctx->sMain != ctx->stream) cudaStreamDestroy(ctx->sMain);
 	if (ctx->sSecond != ctx->stream2) cudaStreamDestroy(ctx->sSecond);
 #ifndef PSC_CPU_SHIM
@@ -550,7 +566,7 @@ int psc_build_constraints(psc_ctx *ctx)
 		bool ok = s.grp_lo.ensure(sizeof(int) * (size_t)(nc + 1)) && s.grp_hi.ensure(sizeof(int) * (size_t)(nc + 1)) &&
 		          s.bits_off.ensure(sizeof(long long) * (size_t)(nc + 1)) && s.n_con.ensure(sizeof(int) * (size_t)(nc + 1)) &&
 		          s.n_pair.ensure(sizeof(int) * (size_t)(nc + 1)) && s.cand_meta.ensure(sizeof(int4) * n) &&
-		          s.cand_cid.ensure(sizeof(int) * n) && s.sortbuf.ensure(sizeof(int) * (2 * n + 64)) &&
+		          s.cand_cid.ensure(sizeof(int) * n) && s.sortbuf.ensure(sizeof(int) * (4 * n + 64)) &&
 		          s.pair_key.ensure(sizeof(uint64_t) * n) && s.pair_uniq_in.ensure(sizeof(int) * n) &&
 		          s.con_first.ensure(sizeof(int) * n) && s.con_last.ensure(sizeof(int) * n) &&
 		          s.con_support.ensure(sizeof(int) * n) && s.con_uniq.ensure(sizeof(int) * n) &&
@@ -631,7 +647,17 @@ int psc_build_constraints(psc_ctx *ctx)
 		for (int si = 0; si < S; ++si)
 			for (int c = 0; c < nc; ++c)
 				sz[(size_t)si * nc + c] = ctx->samples[(size_t)si].h_hi[(size_t)c] - ctx->samples[(size_t)si].h_lo[(size_t)c];
-		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sz[(size_t)a] > sz[(size_t)b]; });
+		// largest first is a scheduling hint: buckets by bit length instead of a comparison sort of S * n_comp units
+		size_t cnt[34] = {0};
+		std::vector<unsigned char> bucket((size_t)nUnits);
+		for (int u = 0; u < nUnits; ++u) {
+			int v = sz[(size_t)u], b = 0;
+			while (v > 0) { v >>= 1; ++b; }
+			bucket[(size_t)u] = (unsigned char)(32 - b);
+			++cnt[bucket[(size_t)u] + 1];
+		}
+		for (int b = 0; b < 33; ++b) cnt[b + 1] += cnt[b];
+		for (int u = 0; u < nUnits; ++u) order[cnt[bucket[(size_t)u]]++] = u;
 	}
 	std::vector<SampleDev> hs((size_t)S);
 	for (int si = 0; si < S; ++si) hs[(size_t)si] = ctx->samples[(size_t)si].d;

@@ -101,18 +101,33 @@ __global__ void __launch_bounds__(128, PSC_DP2_MINBLOCKS) k_dp2_units(GraphDev g
 	}
 }
 
+#define PSC_MERGE_SORT_CAP 2048
 __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const DpUnit *units, const int *compList, int nComp,
                                                   const int *n_tx, const char *txArena, char *scratch, const long long *scr_off,
                                                   int *counter, int width)
 {
 	Coop co = make_coop(width);
 	int S = sv.prm.S;
+	// sort buffer of CoalesceSameTranscripts: 2048 (prefix | index) words per warp in shared memory
+	uint64_t *sort64 = nullptr;
+	int sort64Cap = 0;
+#ifndef PSC_CPU_SHIM
+	extern __shared__ __align__(16) uint64_t merge_smem[]; // 4 * PSC_MERGE_SORT_CAP words (dynamic: 64 KB)
+	if (width == 32) {
+		sort64 = merge_smem + (threadIdx.x >> 5) * PSC_MERGE_SORT_CAP;
+		sort64Cap = PSC_MERGE_SORT_CAP;
+	}
+#else
+	static thread_local uint64_t merge_host[PSC_MERGE_SORT_CAP];
+	sort64 = merge_host;
+	sort64Cap = PSC_MERGE_SORT_CAP;
+#endif
 	for (;;) {
 		int k = 0;
 		if (co.lane == 0) k = atomic_add(counter, 1);
 		k = co.bcast(k, 0);
 		if (k >= nComp) break;
-		dp_merge(co, g, sv, compList[k], units, k * S, n_tx, txArena, scratch + scr_off[k]);
+		dp_merge(co, g, sv, compList[k], units, k * S, n_tx, txArena, scratch + scr_off[k], sort64, sort64Cap);
 		co.sync();
 	}
 }
@@ -427,7 +442,23 @@ int psc_solve(psc_ctx *ctx)
 				c0 = c1;
 				continue;
 			}
-			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+			if (order.size() > 65536) {
+				// heaviest first is only a scheduling hint: bucket by the bit length of the cost instead of a full sort
+				std::vector<int> bucketOf(order.size());
+				size_t cnt64[66] = {0};
+				for (size_t q = 0; q < order.size(); ++q) {
+					long long cq = cost[(size_t)order[q]];
+					int b = 0;
+					while (cq > 0) { cq >>= 1; ++b; }
+					bucketOf[q] = 64 - b; // 0: heaviest
+					++cnt64[bucketOf[q] + 1];
+				}
+				for (int b = 0; b < 65; ++b) cnt64[b + 1] += cnt64[b];
+				std::vector<int> sorted(order.size());
+				for (size_t q = 0; q < order.size(); ++q) sorted[cnt64[bucketOf[q]]++] = order[q];
+				order.swap(sorted);
+			} else
+				std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
 			ok = ub.scratch.ensure((size_t)sAcc + 16) && ub.pred.ensure((size_t)pAcc + 16) &&
 			     upload(ctx, ub.scr_off, scrOff.data(), scrOff.size(), strm) && upload(ctx, ub.pred_off, predOff.data(), predOff.size(), strm) &&
 			     upload(ctx, ub.order, order.data(), order.size(), strm) && ub.n_pred.ensure(sizeof(int) * (size_t)nUnits) &&
@@ -692,8 +723,21 @@ int psc_solve(psc_ctx *ctx)
 		    !upload(ctx, db.dp_scr_off, pd.mergeOff.data(), pd.mergeOff.size(), strm))
 			return ctx->fail("out of device memory (DP merge)");
 		CK(cudaMemsetAsync(cnt, 0, 32, strm));
+#ifndef PSC_CPU_SHIM
+		{
+			const size_t smemBytes = ctx->coop == 32 ? 4 * PSC_MERGE_SORT_CAP * sizeof(uint64_t) : 0;
+			CK(cudaFuncSetAttribute(k_dp_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PSC_MERGE_SORT_CAP * (int)sizeof(uint64_t)));
+			std::lock_guard<std::mutex> lk_(ctx->launchMu);
+			ctx->ktime_begin(7, strm);
+			k_dp_merge<<<launch_grid(ctx, pd.nComp), 128, smemBytes, strm>>>(ctx->gd, sv, db.dp_units.as<DpUnit>(), db.list.as<int>(), pd.nComp,
+			                                                                 db.dp_ntx.as<int>(), (const char *)db.dp_tx.p, (char *)db.dp_merge_scr.p,
+			                                                                 db.dp_scr_off.as<long long>(), cnt, ctx->coop);
+			ctx->ktime_end();
+		}
+#else
 		KLAUNCH_ON(strm, 7, k_dp_merge, launch_grid(ctx, pd.nComp), 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.list.as<int>(), pd.nComp,
 		           db.dp_ntx.as<int>(), (const char *)db.dp_tx.p, (char *)db.dp_merge_scr.p, db.dp_scr_off.as<long long>(), cnt, ctx->coop);
+#endif
 		++launches;
 		CK(cudaGetLastError());
 		return 0;
@@ -711,6 +755,7 @@ int psc_solve(psc_ctx *ctx)
 			std::vector<long long> cost;
 			long long tAcc = 0, mAcc = 0;
 			size_t arenaBytes = 0, hotWanted = 0;
+			std::vector<size_t> smallNeed; // per unit: arena bytes when run one thread per unit (0: not eligible)
 			size_t i1 = i0;
 			while (i1 < comps.size()) {
 				int c = comps[i1];
@@ -757,6 +802,8 @@ int psc_solve(psc_ctx *ctx)
 				long long mNeed = (long long)dp_merge_layout(nullptr, nullptr, W, cap);
 				if (i1 > i0 && (size_t)(tAcc + tNeed + mAcc + mNeed) > ctx->mem_budget) break;
 				for (auto &u : mine) {
+					const int Cu = ctx->samples[(size_t)u.sample].h_ncon[(size_t)c];
+					smallNeed.push_back(n <= 64 ? dp2_layout(nullptr, nullptr, nullptr, 0, nullptr, 0, n, ctx->h_next_cnt[(size_t)c], std::max(Cu, 100), 3 * n + 32) : 0);
 					// algorithmic bytes of the DP kernel: the sample's constraint table read once, its transcript list written once
 					dpBytes += (long long)ctx->samples[(size_t)u.sample].h_ncon[(size_t)c] * (8LL * W + 40) + (long long)u.iterBound * (8LL * W + 8);
 					pd.units.push_back(u);
@@ -798,8 +845,31 @@ int psc_solve(psc_ctx *ctx)
 					hotCrit = std::min<size_t>((hotCrit + 1023) & ~(size_t)1023, 110 << 10);
 				}
 			}
+			// The bulk launch hands the light end of its list to a one-thread-per-unit launch: the interpreter is scalar per
+			// unit (the lanes of a warp only cooperate in the list building and the assignment scans), so for throughput
+			// 32 units per warp beat one; the heavy end stays one unit per warp, where latency counts (PSC_DP_T1_FRAC).
+			int nT1 = 0;
+			size_t arenaT1 = 0;
+			if (ctx->coop == 32 && !heavyLaunch && useV2 && !dpDbg && nUnits >= 4096) {
+				double frac = 0.0; // measured on B200: one thread per unit is slower (divergence, uncoalesced tables); kept as a switch
+				if (const char *e = getenv("PSC_DP_T1_FRAC")) frac = atof(e);
+				const int firstT1 = nUnits - (int)(frac * nUnits);
+				std::vector<int> keepW, goT1;
+				for (int k = 0; k < nUnits; ++k) {
+					int u = order[(size_t)k];
+					if (k >= firstT1 && smallNeed[(size_t)u] > 0) {
+						goT1.push_back(u);
+						arenaT1 = std::max(arenaT1, smallNeed[(size_t)u]);
+					} else
+						keepW.push_back(u);
+				}
+				nT1 = (int)goT1.size();
+				order = keepW;
+				order.insert(order.end(), goT1.begin(), goT1.end());
+				arenaT1 = (arenaT1 + 255) & ~(size_t)255;
+			}
 			const long long groupsPerBlock = threads / ctx->coop;
-			const int nBulk = nUnits - nCrit;
+			const int nBulk = nUnits - nCrit - nT1;
 			long long blocks = (nBulk + groupsPerBlock - 1) / groupsPerBlock;
 			{
 				long long blocksPerSm = PSC_DP2_MINBLOCKS;
@@ -809,8 +879,14 @@ int psc_solve(psc_ctx *ctx)
 				blocks = std::max<long long>(1, std::min(blocks, fit));
 			}
 			const size_t bulkArenas = (size_t)blocks * (size_t)groupsPerBlock;
+			long long blocksT1 = 0;
+			if (nT1 > 0) {
+				blocksT1 = std::min<long long>((nT1 + 127) / 128, (long long)ctx->n_sm * PSC_DP2_MINBLOCKS);
+				blocksT1 = std::max<long long>(1, std::min<long long>(blocksT1, (long long)(ctx->mem_budget / (arenaT1 * 128))));
+			}
+			const size_t t1Off = (bulkArenas + (size_t)nCrit) * arenaBytes;
 			if (!db.dp_tx.ensure((size_t)tAcc + 16) || !db.dp_ntx.ensure(sizeof(int) * (size_t)(nUnits + 1)) || !db.dp_ovf.ensure(64) ||
-			    !db.dp_arena.ensure((bulkArenas + (size_t)nCrit) * arenaBytes + 16))
+			    !db.dp_arena.ensure(t1Off + (size_t)blocksT1 * 128 * arenaT1 + 16))
 				return ctx->fail("out of device memory (DP program arenas)");
 			CK(cudaMemsetAsync(db.dp_ntx.p, useV2 ? 0 : 0xff, sizeof(int) * (size_t)(nUnits + 1), strm));
 			CK(cudaMemsetAsync(db.dp_ovf.p, 0, 64, strm));
@@ -840,6 +916,17 @@ int psc_solve(psc_ctx *ctx)
 					CK(cudaEventRecord(ctx->evCritDone, ctx->sCrit));
 					++launches;
 				}
+				if (nT1 > 0) {
+					CK(cudaEventRecord(ctx->evT1Go, strm));
+					CK(cudaStreamWaitEvent(ctx->sThird, ctx->evT1Go, 0));
+					ctx->ktime_begin(11, ctx->sThird);
+					k_dp2_units<<<(int)blocksT1, 128, 0, ctx->sThird>>>(ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>() + nCrit + nBulk, nT1,
+					                                                 (char *)db.dp_arena.p + t1Off, arenaT1, 0, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt + 5,
+					                                                 db.dp_ovf.as<int>(), 1, dbgPtr);
+					ctx->ktime_end();
+					CK(cudaEventRecord(ctx->evT1Done, ctx->sThird));
+					++launches;
+				}
 				if (nBulk > 0) {
 					ctx->ktime_begin(10, strm);
 					k_dp2_units<<<(int)blocks, threads, hotBytes * (size_t)(threads / 32), strm>>>(
@@ -848,6 +935,7 @@ int psc_solve(psc_ctx *ctx)
 					ctx->ktime_end();
 				}
 				if (nCrit > 0) CK(cudaStreamWaitEvent(strm, ctx->evCritDone, 0));
+				if (nT1 > 0) CK(cudaStreamWaitEvent(strm, ctx->evT1Done, 0));
 #else
 				KLAUNCH_ON(strm, 10, k_dp2_units, (int)blocks, threads, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nUnits,
 				           (char *)db.dp_arena.p, arenaBytes, hotBytes, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, db.dp_ovf.as<int>(), ctx->coop, dbgPtr);
@@ -910,7 +998,7 @@ int psc_solve(psc_ctx *ctx)
 		const cudaStream_t sHeavy = ctx->critSms > 0 ? ctx->sCrit : ctx->sMain;
 		if (dp_launch(heavy, sHeavy, st.db[0], counter, pdH, true) != 0) return 1;
 		if (dp_launch(rest, ctx->sSecond, st.db[1], counter + 8, pdR, false) != 0) return 1;
-		ResultSet resR, resH;
+		ResultSet &resR = st.passR, &resH = st.passH;
 		resR.reset();
 		resH.reset();
 		int rcR = 0;

@@ -249,12 +249,40 @@ template <class Less> PSC_DEV void coop_sort(const Coop &co, int *idx, int n, Le
 	}
 }
 
+// the same network over 64-bit elements (slots >= n hold ~0 == +infinity): used with (sort prefix | index) words
+template <class Less> PSC_DEV void coop_sort64(const Coop &co, uint64_t *v, int n, Less less)
+{
+	if (n <= 1) return;
+	int P = next_pow2(n);
+	for (int i = n + co.lane; i < P; i += co.n) v[i] = ~(uint64_t)0;
+	co.sync();
+	for (int k = 2; k <= P; k <<= 1) {
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int t = co.lane; t < (P >> 1); t += co.n) {
+				int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+				int l = i | j;
+				uint64_t a = v[i], b = v[l];
+				bool up = (i & k) == 0;
+				uint64_t x = up ? a : b, y = up ? b : a;
+				bool x_gt_y = (x == ~(uint64_t)0) ? (y != ~(uint64_t)0) : (y == ~(uint64_t)0 ? false : less(y, x));
+				if (x_gt_y) {
+					v[i] = b;
+					v[l] = a;
+				}
+			}
+			co.sync();
+		}
+	}
+}
+
 #ifdef PSC_CPU_SHIM
 template <class T> static inline T atomic_add(T *p, T v) { T o = *p; *p = o + v; return o; }
 static inline int atomic_max(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline int atomic_cas(int *p, int expect, int v) { int o = *p; if (o == expect) *p = v; return o; }
 #else
 template <class T> PSC_DEV T atomic_add(T *p, T v) { return atomicAdd(p, v); }
 PSC_DEV int atomic_max(int *p, int v) { return atomicMax(p, v); }
+PSC_DEV int atomic_cas(int *p, int expect, int v) { return atomicCAS(p, expect, v); }
 #endif
 
 } // namespace pscdev

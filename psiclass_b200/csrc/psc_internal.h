@@ -44,7 +44,7 @@ struct SampleDev {
 	int4 *cand_meta;     // first (-1: rejected), last, maxReadLen, nh | uniq<<8 | mate kind<<16
 	int *cand_cid;       // constraint id of the read
 	uint64_t *cand_bits; // [bits_off[n_comp]]
-	int *sortbuf;        // [2 * n_reads + 64]
+	int *sortbuf;        // [4 * n_reads + 64]: 4R ints of scratch per group (hash tables, NH = 3 sort order)
 	uint64_t *pair_key;  // [n_reads]
 	int *pair_uniq_in;   // [n_reads]
 

@@ -52,6 +52,7 @@ struct SolveState : ResultSet {
 		db[1].scratch = &dp_rest_scratch;
 	}
 	std::vector<int> h_at_cnt, h_use_dp, h_n_cand;
+	ResultSet passR, passH; // per-pass results (kept across calls: no reallocation, no page faults after the first step)
 	// results, host side (filled chunk by chunk): the ResultSet base
 	void release()
 	{
