@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <memory>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -439,6 +441,9 @@ void ReadAccumulator::finish()
 	}
 }
 
+// Single pass over one BAM: the BGZF blocks are inflated by `threads` workers, in order, into one image while this
+// thread already parses the records behind them (alignments.hpp:146-277 and :489-571 need one sequential reader; the
+// inflate, which is most of the time, does not).
 bool decode_bam(const std::string &path, int threads, SampleReads &out, std::string &err)
 {
 	std::vector<uint8_t> f;
@@ -448,22 +453,95 @@ bool decode_bam(const std::string &path, int threads, SampleReads &out, std::str
 	uint64_t total = 0;
 	if (!index_blocks(f, blocks, total, err))
 		return false;
-	std::vector<uint8_t> u;
-	if (!inflate_all(f, blocks, total, threads, u, err))
-		return false;
-	std::vector<uint8_t>().swap(f);
+	std::unique_ptr<uint8_t[]> image(new uint8_t[total + 8]); // not zero-filled: every byte is written by the inflate
+	const size_t CHUNK = 64;                                  // blocks per unit of work (~4 MB inflated)
+	const size_t nChunks = (blocks.size() + CHUNK - 1) / CHUNK;
+	std::unique_ptr<std::atomic<unsigned char>[]> chunkDone(new std::atomic<unsigned char>[nChunks + 1]);
+	for (size_t k = 0; k <= nChunks; ++k) chunkDone[k].store(0, std::memory_order_relaxed);
+	std::atomic<size_t> next(0);
+	std::atomic<bool> ok(true);
+	auto work = [&]() {
+		z_stream zs;
+		memset(&zs, 0, sizeof(zs));
+		bool init = inflateInit2(&zs, -15) == Z_OK;
+		for (;;) {
+			size_t k = next.fetch_add(1);
+			if (k >= nChunks) break;
+			size_t i = k * CHUNK, e = std::min(blocks.size(), i + CHUNK);
+			for (; i < e && init; ++i) {
+				const Block &b = blocks[i];
+				if (b.isize == 0) continue;
+				inflateReset(&zs);
+				zs.next_in = const_cast<uint8_t *>(f.data() + b.coff);
+				zs.avail_in = b.clen;
+				zs.next_out = image.get() + b.uoff;
+				zs.avail_out = b.isize;
+				int rc = inflate(&zs, Z_FINISH);
+				if (!(rc == Z_STREAM_END && zs.avail_out == 0)) ok = false;
+			}
+			if (!init) ok = false;
+			chunkDone[k].store(1, std::memory_order_release);
+		}
+		if (init) inflateEnd(&zs);
+	};
+	std::vector<std::thread> pool;
+	for (int t = 0; t < std::max(1, threads); ++t) pool.emplace_back(work);
+	struct Joiner {
+		std::vector<std::thread> &p;
+		~Joiner() { for (auto &t : p) if (t.joinable()) t.join(); }
+	} joiner{pool};
+	// bytes [0, ready) of the image are final
+	size_t frontChunk = 0;
+	uint64_t ready = 0;
+	auto wait_for = [&](uint64_t need) -> bool {
+		while (ready < need) {
+			if (frontChunk >= nChunks) return false;
+			if (chunkDone[frontChunk].load(std::memory_order_acquire)) {
+				++frontChunk;
+				size_t b = std::min(blocks.size(), frontChunk * CHUNK);
+				ready = b < blocks.size() ? blocks[b].uoff : total;
+			} else
+				std::this_thread::sleep_for(std::chrono::microseconds(50));
+		}
+		return true;
+	};
+	const uint8_t *ubase = image.get();
+	const size_t usize = (size_t)total;
 
 	out = SampleReads();
 	out.path = path;
 	size_t off = 0;
-	if (!parse_header(u.data(), u.size(), off, out.chr_names, out.chr_len, err))
-		return false;
+	{
+		// the header: magic, l_text, text, n_ref, references -- wait for as much as it needs
+		if (!wait_for(std::min<uint64_t>(total, 12))) { err = "truncated BAM header"; return false; }
+		uint64_t need = 12;
+		if (usize >= 8) need = 12 + (uint64_t)rd32(ubase + 4);
+		if (!wait_for(std::min<uint64_t>(total, need))) { err = "truncated BAM header"; return false; }
+		// the reference list follows the text; its size is only known entry by entry: wait for the whole first chunks
+		// until the parse succeeds
+		for (;;) {
+			size_t o2 = 0;
+			std::vector<std::string> names;
+			std::vector<int32_t> lens;
+			std::string e2;
+			if (parse_header(ubase, (size_t)ready, o2, names, lens, e2)) {
+				off = o2;
+				out.chr_names = names;
+				out.chr_len = lens;
+				break;
+			}
+			if (ready >= total) { err = e2; return false; }
+			if (!wait_for(std::min<uint64_t>(total, ready + 1))) { err = e2; return false; }
+		}
+	}
 	ReadAccumulator acc(out);
-	const uint8_t *base = u.data();
-	size_t n = u.size();
+	const uint8_t *base = ubase;
+	size_t n = usize;
 	std::vector<uint32_t> cigbuf;
 	while (off + 4 <= n) {
+		if (!wait_for(off + 4)) break;
 		uint32_t bs = rd32(base + off);
+		if (off + 4 + (size_t)bs <= n && !wait_for(off + 4 + (size_t)bs)) break;
 		if (off + 4 + bs > n || bs < 32) {
 			err = "truncated BAM record";
 			return false;
@@ -490,6 +568,11 @@ bool decode_bam(const std::string &path, int threads, SampleReads &out, std::str
 		        t != NULL, t ? aux_int(t) : 1);
 	}
 	acc.finish();
+	for (auto &t : pool) t.join();
+	if (!ok) {
+		err = "BGZF inflate failed";
+		return false;
+	}
 	return true;
 }
 

@@ -71,8 +71,15 @@ static double now_s()
 	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Device contexts are created while the BAM files are still being decoded (context creation takes about a second).
+struct EarlyCtx {
+	psc_ctx *ctx = nullptr;
+	int rc = 0;
+	std::thread th;
+};
+
 static void run_shard(int device, const psc::Graph &g, const std::vector<psc::SampleReads> &samples, const psc_params &prm,
-                      Shard &sh)
+                      Shard &sh, EarlyCtx *early)
 {
 	int S = (int)samples.size();
 	int nc = sh.c1 - sh.c0;
@@ -88,7 +95,14 @@ static void run_shard(int device, const psc::Graph &g, const std::vector<psc::Sa
 		sh.prev_off[(size_t)(i - se0)] = g.prev_off[(size_t)i] - pe0;
 	}
 	psc_ctx *ctx = nullptr;
-	int rc = psc_create(&ctx, device);
+	int rc;
+	if (early) {
+		if (early->th.joinable()) early->th.join();
+		ctx = early->ctx;
+		rc = early->rc;
+		early->ctx = nullptr;
+	} else
+		rc = psc_create(&ctx, device);
 	if (rc) {
 		sh.err = "psc_create failed (code " + std::to_string(rc) + "): a CUDA device is required";
 		return;
@@ -258,11 +272,15 @@ int main(int argc, char *argv[])
 	int S = (int)bamPaths.size();
 	if (numThreads < 1) numThreads = 1;
 	const double tStart = now_s();
+	int nGpu = 1;
+	if (const char *e = getenv("PSC_GPUS")) nGpu = std::max(1, atoi(e));
+	std::vector<EarlyCtx> early((size_t)nGpu);
+	for (int d = 0; d < nGpu; ++d) early[(size_t)d].th = std::thread([&early, d]() { early[(size_t)d].rc = psc_create(&early[(size_t)d].ctx, d); });
 	// ---- one decode pass per BAM (library statistics + alignment records), samples in parallel ----
 	std::vector<psc::SampleReads> samples((size_t)S);
 	std::vector<std::string> errs((size_t)S);
 	{
-		int outer = std::min(numThreads, S), inner = std::max(1, numThreads / std::max(1, outer));
+		int outer = std::min(numThreads, S), inner = std::max(1, (numThreads + outer - 1) / std::max(1, outer)); // inflate workers per sample (the parser thread comes on top)
 		std::vector<std::thread> pool;
 		for (int t = 0; t < outer; ++t)
 			pool.emplace_back([&, t]() {
@@ -299,8 +317,7 @@ int main(int argc, char *argv[])
 
 	const double tGraph = now_s();
 	// ---- shard the components over the devices, balanced by an estimate of the device work ----
-	int nGpu = 1;
-	if (const char *e = getenv("PSC_GPUS")) nGpu = std::max(1, atoi(e));
+	const int nGpuAsked = nGpu;
 	nGpu = std::min(nGpu, std::max(1, g.n_comp));
 	// per component and sample: the first read it examines (Constraints.cpp:272-283 in closed form)
 	std::vector<int> maxEnd((size_t)g.n_comp);
@@ -353,8 +370,12 @@ int main(int argc, char *argv[])
 	}
 	{
 		std::vector<std::thread> pool;
-		for (int d = 0; d < nGpu; ++d) pool.emplace_back([&, d]() { run_shard(d, g, samples, prm, shards[(size_t)d]); });
+		for (int d = 0; d < nGpu; ++d) pool.emplace_back([&, d]() { run_shard(d, g, samples, prm, shards[(size_t)d], &early[(size_t)d]); });
 		for (auto &t : pool) t.join();
+	}
+	for (int d = 0; d < nGpuAsked; ++d) { // contexts of devices that got no shard
+		if (early[(size_t)d].th.joinable()) early[(size_t)d].th.join();
+		if (early[(size_t)d].ctx) psc_destroy(early[(size_t)d].ctx);
 	}
 	for (auto &sh : shards)
 		if (!sh.err.empty()) {

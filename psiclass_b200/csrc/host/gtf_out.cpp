@@ -1,8 +1,10 @@
 #include "gtf_out.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 
 namespace psc {
 
@@ -37,38 +39,54 @@ bool write_gtfs(std::vector<OutTx> &q, const std::vector<double> &totalReadCnt, 
 		if (q[a].sample != q[b].sample) return q[a].sample < q[b].sample;
 		return a < b;
 	});
-	std::vector<FILE *> fps(S, nullptr);
-	for (size_t s = 0; s < S; ++s) {
-		std::string path = prefix.empty() ? "sample_" + std::to_string(s) + ".gtf" : prefix + "_sample_" + std::to_string(s) + ".gtf";
-		fps[s] = fopen(path.c_str(), "w");
-		if (!fps[s]) {
-			err = "cannot write " + path;
-			return false;
+	// transcript ids (Flush, TranscriptDecider.hpp:236-256) and the per-sample order of the records
+	std::vector<int> tidOf(q.size(), 0);
+	std::vector<std::vector<size_t>> bySample(S);
+	{
+		int gid = -1, tid = 0;
+		for (size_t i = 0; i < order.size();) {
+			size_t j = i + 1;
+			while (j < order.size() && cmp_tx(q[order[i]], q[order[j]]) == 0) ++j;
+			if (q[order[i]].gene_id != gid) {
+				gid = q[order[i]].gene_id;
+				tid = 0;
+			} else
+				++tid;
+			for (size_t l = i; l < j; ++l) {
+				tidOf[order[l]] = tid;
+				bySample[(size_t)q[order[l]].sample].push_back(order[l]);
+			}
+			i = j;
 		}
-		fprintf(fps[s], "#PsiCLASS_v1.0.3\n#");
-		for (int a = 0; a < argc; ++a) fprintf(fps[s], "%s%s", argv[a], a + 1 < argc ? " " : "\n");
-		const char *base = strrchr(bams[s].c_str(), '/');
-		fprintf(fps[s], "#%s\n", base ? base + 1 : bams[s].c_str());
 	}
+	// one writer thread per sample file (the text is ~140 bytes per exon line: formatting dominates)
 	std::vector<std::vector<VoteTx>> perSample(forVote ? S : 0);
-	int gid = -1, tid = 0;
-	for (size_t i = 0; i < order.size();) {
-		size_t j = i + 1;
-		while (j < order.size() && cmp_tx(q[order[i]], q[order[j]]) == 0) ++j;
-		if (q[order[i]].gene_id != gid) {
-			gid = q[order[i]].gene_id;
-			tid = 0;
-		} else
-			++tid;
-		for (size_t l = i; l < j; ++l) {
-			const OutTx &t = q[order[l]];
+	std::vector<std::string> errs(S);
+	auto writeSample = [&](size_t sIdx) {
+		std::string path = prefix.empty() ? "sample_" + std::to_string(sIdx) + ".gtf" : prefix + "_sample_" + std::to_string(sIdx) + ".gtf";
+		FILE *fp = fopen(path.c_str(), "w");
+		if (!fp) {
+			errs[sIdx] = "cannot write " + path;
+			return;
+		}
+		std::vector<char> iobuf(1 << 20);
+		setvbuf(fp, iobuf.data(), _IOFBF, iobuf.size());
+		fprintf(fp, "#PsiCLASS_v1.0.3\n#");
+		for (int a = 0; a < argc; ++a) fprintf(fp, "%s%s", argv[a], a + 1 < argc ? " " : "\n");
+		const char *baseName = strrchr(bams[sIdx].c_str(), '/');
+		fprintf(fp, "#%s\n", baseName ? baseName + 1 : bams[sIdx].c_str());
+		char tail[160];
+		for (size_t idx : bySample[sIdx]) {
+			const OutTx &t = q[idx];
+			const int tid = tidOf[idx];
 			const char *c = chr[(size_t)t.chr].c_str();
-			FILE *fp = fps[(size_t)t.sample];
-			fprintf(fp, "%s\tPsiCLASS\ttranscript\t%d\t%d\t1000\t%c\t.\tgene_id \"%s.%d\"; transcript_id \"%s.%d.%d\"; FPKM \"%.6lf\"; TPM \"%.6lf\"; cov \"%.6lf\";\n",
-			        c, t.exons[0].first, t.exons.back().second, t.strand, c, t.gene_id, c, t.gene_id, tid, t.fpkm, t.tpm, t.cov);
+			// the part every line of the transcript shares
+			snprintf(tail, sizeof(tail), "FPKM \"%.6lf\"; TPM \"%.6lf\"; cov \"%.6lf\";\n", t.fpkm, t.tpm, t.cov);
+			fprintf(fp, "%s\tPsiCLASS\ttranscript\t%d\t%d\t1000\t%c\t.\tgene_id \"%s.%d\"; transcript_id \"%s.%d.%d\"; %s", c, t.exons[0].first,
+			        t.exons.back().second, t.strand, c, t.gene_id, c, t.gene_id, tid, tail);
 			for (size_t e = 0; e < t.exons.size(); ++e)
-				fprintf(fp, "%s\tPsiCLASS\texon\t%d\t%d\t1000\t%c\t.\tgene_id \"%s.%d\"; transcript_id \"%s.%d.%d\"; exon_number \"%d\"; FPKM \"%.6lf\"; TPM \"%.6lf\"; cov \"%.6lf\";\n",
-				        c, t.exons[e].first, t.exons[e].second, t.strand, c, t.gene_id, c, t.gene_id, tid, (int)e + 1, t.fpkm, t.tpm, t.cov);
+				fprintf(fp, "%s\tPsiCLASS\texon\t%d\t%d\t1000\t%c\t.\tgene_id \"%s.%d\"; transcript_id \"%s.%d.%d\"; exon_number \"%d\"; %s", c,
+				        t.exons[e].first, t.exons[e].second, t.strand, c, t.gene_id, c, t.gene_id, tid, (int)e + 1, tail);
 			if (forVote) {
 				VoteTx v;
 				v.sample = t.sample;
@@ -80,12 +98,30 @@ bool write_gtfs(std::vector<OutTx> &q, const std::vector<double> &totalReadCnt, 
 				v.fpkm = gtf_rounded(t.fpkm);
 				v.tpm = gtf_rounded(t.tpm);
 				v.cov = gtf_rounded(t.cov);
-				perSample[(size_t)t.sample].push_back(std::move(v));
+				perSample[sIdx].push_back(std::move(v));
 			}
 		}
-		i = j;
+		fclose(fp);
+	};
+	{
+		size_t nThreads = std::min<size_t>(S, std::max(1u, std::thread::hardware_concurrency()));
+		std::vector<std::thread> pool;
+		std::atomic<size_t> next{0};
+		for (size_t t = 0; t < nThreads; ++t)
+			pool.emplace_back([&]() {
+				for (;;) {
+					size_t sIdx = next.fetch_add(1);
+					if (sIdx >= S) break;
+					writeSample(sIdx);
+				}
+			});
+		for (auto &th : pool) th.join();
 	}
-	for (FILE *fp : fps) fclose(fp);
+	for (auto &e : errs)
+		if (!e.empty()) {
+			err = e;
+			return false;
+		}
 	if (forVote)
 		for (auto &ps : perSample)
 			for (auto &v : ps) forVote->push_back(std::move(v));

@@ -137,8 +137,11 @@ __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const
 #ifndef PSC_UNITS_MINBLOCKS
 #define PSC_UNITS_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, PSC_UNITS_MINBLOCKS) k_units(GraphDev g, SolveDev sv, ChunkDev ch, int phase, const int *list, int nList,
-                                               int *counter, int width, long long *dbg)
+// One kernel per phase (the phase is a template parameter): each phase's code is tens of thousands of instructions and
+// the launches were instruction-fetch bound (ncu: `no_instruction` the top stall) while one kernel carried all three.
+template <int PHASE>
+__global__ void __launch_bounds__(128, PSC_UNITS_MINBLOCKS) k_units(GraphDev g, SolveDev sv, ChunkDev ch, const int *list, int nList,
+                                                                   int *counter, int width, long long *dbg)
 {
 	Coop co = make_coop(width);
 	int S = sv.prm.S;
@@ -150,11 +153,11 @@ __global__ void __launch_bounds__(128, PSC_UNITS_MINBLOCKS) k_units(GraphDev g, 
 		int ul = list[u];
 		int c = ch.c0 + ul / S, s = ul % S;
 		long long t0 = dbg ? clock64() : 0;
-		if (phase == 1) unit_pick_round1(co, g, sv, ch, c, s);
-		else if (phase == 2) unit_pick_round2(co, g, sv, ch, c, s);
+		if (PHASE == 1) unit_pick_round1(co, g, sv, ch, c, s);
+		else if (PHASE == 2) unit_pick_round2(co, g, sv, ch, c, s);
 		else unit_rescue(co, g, sv, ch, c, s);
 		co.sync();
-		if (dbg && co.lane == 0) dbg[(long long)ul * 3 + (phase - 1)] = clock64() - t0; // PSC_DEBUG_UNITS
+		if (dbg && co.lane == 0) dbg[(long long)ul * 3 + (PHASE - 1)] = clock64() - t0; // PSC_DEBUG_UNITS
 	}
 }
 
@@ -486,7 +489,9 @@ int psc_solve(psc_ctx *ctx)
 			}
 			for (int phase = 1; phase <= 3; ++phase) {
 				CK(cudaMemsetAsync(cnt, 0, 32, strm));
-				KLAUNCH_ON(strm, phase == 1 ? 5 : (phase == 2 ? 8 : 9), k_units, launch_grid(ctx, nList), 128, ctx->gd, sv, ch, phase, ub.order.as<int>(), nList, cnt, ctx->coop, unitDbg);
+				if (phase == 1) KLAUNCH_ON(strm, 5, k_units<1>, launch_grid(ctx, nList), 128, ctx->gd, sv, ch, ub.order.as<int>(), nList, cnt, ctx->coop, unitDbg);
+				else if (phase == 2) KLAUNCH_ON(strm, 8, k_units<2>, launch_grid(ctx, nList), 128, ctx->gd, sv, ch, ub.order.as<int>(), nList, cnt, ctx->coop, unitDbg);
+				else KLAUNCH_ON(strm, 9, k_units<3>, launch_grid(ctx, nList), 128, ctx->gd, sv, ch, ub.order.as<int>(), nList, cnt, ctx->coop, unitDbg);
 				++launches;
 				CK(cudaGetLastError());
 				if (hostDbg) {
@@ -970,9 +975,10 @@ int psc_solve(psc_ctx *ctx)
 			}
 			std::sort(byC.begin(), byC.end());
 			// the heavy chain runs in the critical SM partition: as many components as keep its (component, sample) units
-			// at about four per critical SM (PSC_HEAVY_COMPS overrides); without partitioning, 1/16 of the DP components
+			// at about twelve per critical SM (PSC_HEAVY_COMPS overrides; measured best on the bench workload: 16 SMs, 20
+			// components of 10 samples); without partitioning, 1/16 of the DP components
 			size_t nH = std::min<size_t>(std::max<size_t>(dpList.size() / 16, 1), (size_t)ctx->n_sm);
-			if (ctx->critSms > 0) nH = std::max<size_t>(1, std::min<size_t>(nH, (size_t)(4 * ctx->critSms / std::max(1, S))));
+			if (ctx->critSms > 0) nH = std::max<size_t>(1, std::min<size_t>(nH, (size_t)(12 * ctx->critSms / std::max(1, S))));
 			if (const char *e = getenv("PSC_HEAVY_COMPS")) nH = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), dpList.size() - 1));
 			if (forced && dpList.size() < 64) nH = std::max<size_t>(dpList.size() / 4, 1);
 			std::vector<char> isH((size_t)nc, 0);
