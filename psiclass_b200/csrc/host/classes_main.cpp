@@ -210,7 +210,8 @@ static void run_shard(int device, const psc::Graph &g, const std::vector<psc::Sa
 		for (int64_t e = eo[(size_t)k]; e < eo[(size_t)k + 1]; ++e) o.exons.push_back({es[(size_t)e], ee[(size_t)e]});
 	}
 	sh.download_s = now_s() - t3;
-	psc_destroy(ctx);
+	// the context is left to process exit: freeing its buffers one by one costs most of a second per device
+	(void)ctx;
 #undef E
 }
 
@@ -276,6 +277,16 @@ int main(int argc, char *argv[])
 	if (const char *e = getenv("PSC_GPUS")) nGpu = std::max(1, atoi(e));
 	std::vector<EarlyCtx> early((size_t)nGpu);
 	for (int d = 0; d < nGpu; ++d) early[(size_t)d].th = std::thread([&early, d]() { early[(size_t)d].rc = psc_create(&early[(size_t)d].ctx, d); });
+	// ---- the subexon graph is parsed while the BAMs decode (it only needs the chromosome names of BAM #0's header) ----
+	psc::Graph g;
+	std::string graphErr;
+	bool graphOk = false;
+	std::thread graphThread([&]() {
+		std::vector<std::string> names;
+		std::vector<int32_t> lens;
+		if (!psc::read_bam_header(bamPaths[0], names, lens, graphErr)) return;
+		graphOk = psc::load_subexon_graph(subexonPath, names, classifierThreshold, g, graphErr);
+	});
 	// ---- one decode pass per BAM (library statistics + alignment records), samples in parallel ----
 	std::vector<psc::SampleReads> samples((size_t)S);
 	std::vector<std::string> errs((size_t)S);
@@ -296,10 +307,10 @@ int main(int argc, char *argv[])
 			exit(1);
 		}
 	const double tDecoded = now_s();
-	psc::Graph g;
+	graphThread.join();
 	std::string err;
-	if (!psc::load_subexon_graph(subexonPath, samples[0].chr_names, classifierThreshold, g, err)) {
-		printf("%s\n", err.c_str());
+	if (!graphOk) {
+		printf("%s\n", graphErr.c_str());
 		exit(1);
 	}
 	psc_params prm;
