@@ -37,6 +37,19 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(seed=1001, n_chr=24, n_genes=60000, n_samples=10, mean_pairs=60.0)
 CPU_SAMPLE = dict(seed=1001, n_chr=24, n_genes=1500, n_samples=10, mean_pairs=60.0)
+# BASELINE.json configs[2..4] at a stated scale (file legs only: `python bench.py --config K --gpus N [--with-reference]`).
+# Full size is 60000 gene models x 100 samples (configs[2]), 2000 dense components (configs[3]), 30 samples (configs[4]);
+# the scales below keep the reference's CPU pass at minutes (its dense-gene pass runs ~20 s per component).
+EXTRA_CONFIGS = {
+    2: dict(name="configs[2] scaled: 100 samples, 1/10 of the graph (6000 gene models), ~40 read pairs/component/sample",
+            synth=dict(seed=1002, n_chr=24, n_genes=6000, n_samples=100, mean_pairs=40.0), args=[]),
+    3: dict(name="configs[3] scaled: 96 dense components of 200-600 subexons, 10 samples, depth x5, --maxDpConstraintSize -1",
+            synth=dict(seed=1003, n_chr=4, n_genes=96, n_samples=10, dense=1, mean_pairs=300.0), args=["--maxDpConstraintSize", "-1"],
+            ref_genes=8),
+    4: dict(name="configs[4] scaled: 30 samples, 6000 gene models, rf-stranded flags, 15 % paralog pairs (NH=2 primary + secondary), --primaryParalog",
+            synth=dict(seed=1004, n_chr=24, n_genes=6000, n_samples=30, mean_pairs=60.0, stranded=1, p_paralog=0.15),
+            args=["--primaryParalog", "--stranded", "rf"]),
+}
 METRIC = "subexon-graph components assembled/sec (stage 3, all samples)"
 UNIT = "components/s"
 
@@ -147,7 +160,7 @@ def gtf_digest(d, prefix, n_samples):
     return h.hexdigest(), lines
 
 
-def run_classes(binary, d, prefix, threads, gpus=None, extra_env=None):
+def run_classes(binary, d, prefix, threads, gpus=None, extra_env=None, extra_args=()):
     """One `classes` process on the files in d; returns (seconds, perf dict or None)."""
     env = dict(os.environ)
     perf_path = None
@@ -158,7 +171,7 @@ def run_classes(binary, d, prefix, threads, gpus=None, extra_env=None):
     if extra_env:
         env.update(extra_env)
     cmd = [binary, "--lb", os.path.join(d, "bamlist"), "-s", os.path.join(d, "subexon_combined.out"),
-           "-o", os.path.join(d, prefix), "-p", str(threads)]
+           "-o", os.path.join(d, prefix), "-p", str(threads)] + list(extra_args)
     t0 = time.perf_counter()
     subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True, env=env)
     dt = time.perf_counter() - t0
@@ -187,6 +200,51 @@ def describe(cfg):
         cfg["n_genes"], cfg["n_chr"], cfg["seed"], cfg["n_samples"], int(cfg["mean_pairs"]))
 
 
+def run_extra_config(a):
+    """One workload as files, the drop-in `classes` on --gpus devices (sharded by component), optionally the reference."""
+    ec = EXTRA_CONFIGS[a.config]
+    cores = host_cores()
+    syn = dict(ec["synth"])
+    if a.genes:
+        syn["n_genes"] = a.genes
+    ours = os.path.join(ROOT, "psiclass_b200", "bin", "classes")
+    d, ncomp, nbytes = write_workload_files(syn, cores)
+    line = {"config": ec["name"], "workload": describe(syn) if "dense" not in syn else str(syn), "components": ncomp,
+            "bam_bytes": nbytes, "n_gpus": a.gpus, "host_threads": cores, "unit": UNIT}
+    try:
+        t_new, perf = run_classes(ours, d, "new", cores, gpus=a.gpus, extra_args=ec["args"])
+        digest, glines = gtf_digest(d, "new", syn["n_samples"])
+        line["drop_in"] = {"seconds": t_new, "components_per_s": ncomp / t_new, "gtf_sha256": digest, "gtf_lines": glines}
+        if perf:
+            sh = perf.get("shards", [])
+            line["drop_in"]["phases_s"] = {k: perf.get(k) for k in ("decode_s", "graph_s", "device_s", "gtf_s", "total_s")}
+            if sh:
+                pipe = max(x["upload_s"] + x["constraints_s"] + x["solve_s"] + x["download_s"] for x in sh)
+                line["drop_in"]["device_pipeline"] = {"seconds": pipe, "components_per_s": ncomp / pipe,
+                                                      "solve_s_per_shard": [x["solve_s"] for x in sh],
+                                                      "components_per_shard": [x["components"] for x in sh]}
+        ref, kind = reference_binary()
+        if a.with_reference and ref is not None:
+            rd, rn = d, ncomp
+            if ec.get("ref_genes"):  # the reference needs ~20 s per dense component: a bounded sample of the same generator
+                shutil.rmtree(d, ignore_errors=True)
+                syn2 = dict(syn, n_genes=ec["ref_genes"])
+                d, rn, _ = write_workload_files(syn2, cores)
+                rd = d
+                t2, _ = run_classes(ours, rd, "new", cores, gpus=1, extra_args=ec["args"])
+                line["drop_in_on_reference_sample"] = {"components": rn, "seconds": t2}
+            threads = cores if kind == "reference" else 1
+            t_ref, _ = run_classes(ref, rd, "ref", threads, extra_args=ec["args"])
+            rdig, _ = gtf_digest(rd, "ref", syn["n_samples"])
+            ndig, _ = gtf_digest(rd, "new", syn["n_samples"])
+            line["reference"] = {"kind": kind, "cores": threads, "components": rn, "seconds": t_ref, "components_per_s": rn / t_ref,
+                                 "gtf_identical": rdig == ndig}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,7 +256,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the BAM -> GTF legs through the `classes` binary")
     ap.add_argument("--ref-passes", type=int, default=2, help="timed passes of the reference arm (one pass is ~1-2 min)")
+    ap.add_argument("--config", type=int, default=1, help="2, 3, 4: BAM -> GTF legs of BASELINE.json configs[2..4] at a stated scale")
+    ap.add_argument("--with-reference", action="store_true", help="--config: also time the reference `classes` on the same files")
     a = ap.parse_args()
+    if a.config in EXTRA_CONFIGS:
+        return run_extra_config(a)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
