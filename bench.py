@@ -43,9 +43,9 @@ CPU_SAMPLE = dict(seed=1001, n_chr=24, n_genes=1500, n_samples=10, mean_pairs=60
 EXTRA_CONFIGS = {
     2: dict(name="configs[2] scaled: 100 samples, 1/10 of the graph (6000 gene models), ~40 read pairs/component/sample",
             synth=dict(seed=1002, n_chr=24, n_genes=6000, n_samples=100, mean_pairs=40.0), args=[]),
-    3: dict(name="configs[3] scaled: 96 dense components of 200-600 subexons, 10 samples, depth x5, --maxDpConstraintSize -1",
-            synth=dict(seed=1003, n_chr=4, n_genes=96, n_samples=10, dense=1, mean_pairs=300.0), args=["--maxDpConstraintSize", "-1"],
-            ref_genes=8),
+    3: dict(name="configs[3] scaled: 32 dense components of 200-600 subexons, 10 samples, depth x5, --maxDpConstraintSize -1",
+            synth=dict(seed=1003, n_chr=4, n_genes=32, n_samples=10, dense=1, mean_pairs=300.0), args=["--maxDpConstraintSize", "-1"],
+            ref_genes=4),
     4: dict(name="configs[4] scaled: 30 samples, 6000 gene models, rf-stranded flags, 15 % paralog pairs (NH=2 primary + secondary), --primaryParalog",
             synth=dict(seed=1004, n_chr=24, n_genes=6000, n_samples=30, mean_pairs=60.0, stranded=1, p_paralog=0.15),
             args=["--primaryParalog", "--stranded", "rf"]),

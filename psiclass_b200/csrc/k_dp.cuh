@@ -1035,7 +1035,7 @@ PSC_DEVN void dp_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv
 // memory; if they outgrow the slice it starts over with everything in the arena; a unit whose key / frame / list
 // tables outgrow that too reports *n_tx_out = -1 and is redone by the walk engine.
 PSC_DEVN void dp2_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &sv, const DpUnit &u, char *arena, size_t arenaBytes,
-                            char *hot, size_t hotBytes, char *txBase, int *n_tx_out, long long *dbg)
+                            char *hot, size_t hotBytes, char *txBase, int *n_tx_out, long long *dbg, int roomy = 0)
 {
 	DpState st;
 	st.nStates = st.nLevels = st.nIters = st.nFrames = st.nRoots = st.cycRoot = st.cycAssign = 0;
@@ -1051,10 +1051,10 @@ PSC_DEVN void dp2_unit_pick(const Coop &co, const GraphDev &g, const SolveDev &s
 	int inShared = 0;
 	// shared memory is tried only when the slice holds the tables of a typical unit of this size (~1.4 n keys on the
 	// bench workload): an attempt that overflows is thrown away
-	const bool trySmem = hot && dp2_hot_fixed(v.n, v.W) + (size_t)(3 * v.n / 2 + 8) * dp2_hot_per_key(v.W, DP2_FR_PER_KEY_SMEM) <= hotBytes;
+	const bool trySmem = !roomy && hot && dp2_hot_fixed(v.n, v.W) + (size_t)(3 * v.n / 2 + 8) * dp2_hot_per_key(v.W, DP2_FR_PER_KEY_SMEM) <= hotBytes;
 	for (int attempt = trySmem ? 0 : 1; attempt < 2; ++attempt) {
 		char *h = attempt == 0 ? hot : nullptr;
-		size_t used = dp2_layout(&st.d, &z, arena, arenaBytes, h, hotBytes, v.n, E, Ccap);
+		size_t used = dp2_layout(&st.d, &z, arena, arenaBytes, h, hotBytes, v.n, E, Ccap, 0, roomy ? DP2_FR_PER_KEY_ROOMY : DP2_FR_PER_KEY_GLOBAL);
 		if (used > arenaBytes || z.maxKeys < 8 || (h && z.hotBytesUsed > hotBytes)) continue; // does not even hold the fixed part
 		inShared = h != nullptr;
 		for (int k = co.lane; k < v.n + 1; k += co.n) z.key1[k] = -1;

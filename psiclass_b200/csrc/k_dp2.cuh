@@ -84,6 +84,7 @@ struct Dp2 {
 // the compatibility lists, the compiler's walk stack and the per-threshold result cache -- always global.
 #define DP2_FR_PER_KEY_SMEM 3
 #define DP2_FR_PER_KEY_GLOBAL 6
+#define DP2_FR_PER_KEY_ROOMY 24 // second attempt of a unit that outgrew its arena (long untruncated constraints: ~10 frames per key)
 #define DP2_LIST_PER_KEY 64
 __host__ __device__ inline size_t dp2_hot_fixed(int n, int W)
 {
@@ -101,6 +102,13 @@ __host__ __device__ inline int dp2_wanted_keys(int n)
 	long long k = 8LL * n + 128;
 	return (int)(k > 65536 ? 65536 : k);
 }
+// shared memory a unit is given in a packed launch: room for 2n + 16 keys
+__host__ __device__ inline size_t dp2_smem_slice(int n)
+{
+	int W = (n + 63) >> 6;
+	size_t b = dp2_hot_fixed(n, W) + (size_t)(2 * n + 16) * dp2_hot_per_key(W, DP2_FR_PER_KEY_SMEM) + 128;
+	return (b + 127) & ~(size_t)127;
+}
 // shared memory a unit would like: room for 2n + 32 keys (the heaviest units of the bench workload use ~1.4 n)
 __host__ __device__ inline size_t dp2_smem_wanted(int n)
 {
@@ -112,7 +120,7 @@ __host__ __device__ inline size_t dp2_smem_wanted(int n)
 // nullptr (then the hot part follows the cold part in the arena).  With cold == nullptr and coldBytes == 0 returns the
 // arena bytes a unit needs for dp2_wanted_keys(n) keys with everything in global memory.
 __host__ __device__ inline size_t dp2_layout(DpScratch *od, Dp2 *oz, char *cold, size_t coldBytes, char *hot, size_t hotBytes, int n,
-                                             int E, int Cmax, int keysForSizing = 0)
+                                             int E, int Cmax, int keysForSizing = 0, int frPerKeyGlobal = DP2_FR_PER_KEY_GLOBAL)
 {
 	Carver cv(cold);
 	int W = (n + 63) >> 6;
@@ -150,7 +158,7 @@ __host__ __device__ inline size_t dp2_layout(DpScratch *od, Dp2 *oz, char *cold,
 	const size_t coldFixed = (cv.off + 15) & ~(size_t)15;
 	const size_t hotFixed = dp2_hot_fixed(n, W);
 	const bool split = hot != nullptr;
-	const int frPerKey = split ? DP2_FR_PER_KEY_SMEM : DP2_FR_PER_KEY_GLOBAL;
+	const int frPerKey = split ? DP2_FR_PER_KEY_SMEM : frPerKeyGlobal;
 	long long K = keysForSizing > 0 ? keysForSizing : dp2_wanted_keys(n), L;
 	if (coldBytes > 0) {
 		if (split) {

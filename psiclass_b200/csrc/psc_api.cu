@@ -698,6 +698,20 @@ int psc_build_constraints(psc_ctx *ctx)
 	ctx->timing.kernel_bytes[1] = algBytes;
 	ctx->constraints_built = true;
 	ctx->solved = false;
+	// The per-read scratch rows (candidate bit rows, hash-table rows, join keys: ~56 bytes + a bit row per read) are only
+	// needed while the tables are built.  They stay allocated for the next call unless memory is short (less than their
+	// own size left free) or PSC_FREE_SCRATCH=1: then psc_solve gets the room instead.
+	{
+		size_t scratch = 0;
+		for (auto &s : ctx->samples) scratch += s.cand_meta.bytes + s.cand_cid.bytes + s.cand_bits.bytes + s.sortbuf.bytes + s.pair_key.bytes + s.pair_uniq_in.bytes;
+		size_t fr = 0, tot = 0;
+		const char *e = getenv("PSC_FREE_SCRATCH");
+		bool release = e ? atoi(e) != 0 : (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr < scratch);
+		if (release)
+			for (auto &s : ctx->samples) {
+				s.cand_meta.release(); s.cand_cid.release(); s.cand_bits.release(); s.sortbuf.release(); s.pair_key.release(); s.pair_uniq_in.release();
+			}
+	}
 	return 0;
 }
 

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128, PSC_DP_MINBLOCKS) k_dp_units(GraphDev g, 
 #endif
 __global__ void __launch_bounds__(128, PSC_DP2_MINBLOCKS) k_dp2_units(GraphDev g, SolveDev sv, const DpUnit *units, const int *order, int nUnits,
                                                                     char *arenas, size_t arenaBytes, size_t hotBytes, char *txArena, int *n_tx,
-                                                                    int *counter, int *overflow, int width, long long *dbg)
+                                                                    int *counter, int *overflow, int width, long long *dbg, int roomy = 0)
 {
 	Coop co = make_coop(width);
 	char *arena = arenas + (size_t)coop_id(width) * arenaBytes;
@@ -95,13 +95,48 @@ __global__ void __launch_bounds__(128, PSC_DP2_MINBLOCKS) k_dp2_units(GraphDev g
 		u = co.bcast(u, 0);
 		if (u >= nUnits) break;
 		int ui = order[u];
-		dp2_unit_pick(co, g, sv, units[ui], arena, arenaBytes, hot, hotBytes, txArena, n_tx + ui, dbg ? dbg + 8 * (long long)ui : nullptr);
+		dp2_unit_pick(co, g, sv, units[ui], arena, arenaBytes, hot, hotBytes, txArena, n_tx + ui, dbg ? dbg + 8 * (long long)ui : nullptr, roomy);
 		if (co.lane == 0 && n_tx[ui] < 0) atomic_add(overflow, 1);
 		co.sync();
 	}
 }
 
 #define PSC_MERGE_SORT_CAP 2048
+// The same engine, launched over PACKETS: up to four units of similar cost whose shared-memory slices (each sized for
+// its unit, dp2_smem_slice) fit one block's pool together.  Warp w of the block runs unit w of the packet; the block
+// moves to the next packet when all of them are done.  A unit too big for the pool gets no slice (global arena).
+struct DpPacket {
+	int unit[4];     // index into units[], -1: none
+	int hotOff[4];   // byte offset of the unit's slice in the block's pool
+	int hotBytes[4]; // 0: no slice
+};
+#ifndef PSC_CPU_SHIM
+__global__ void __launch_bounds__(128, PSC_DP2_MINBLOCKS) k_dp2_packets(GraphDev g, SolveDev sv, const DpUnit *units, const DpPacket *packets,
+                                                                      int nPackets, char *arenas, size_t arenaBytes, char *txArena, int *n_tx,
+                                                                      int *counter, int *overflow, long long *dbg)
+{
+	Coop co = make_coop(32);
+	char *arena = arenas + (size_t)coop_id(32) * arenaBytes;
+	extern __shared__ __align__(16) unsigned char dp2_pool[];
+	__shared__ int s_packet;
+	const int w = (int)(threadIdx.x >> 5);
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0) s_packet = atomic_add(counter, 1);
+		__syncthreads();
+		const int pk = s_packet;
+		if (pk >= nPackets) break;
+		const DpPacket &P = packets[pk];
+		const int ui = P.unit[w];
+		if (ui >= 0) {
+			char *hot = P.hotBytes[w] > 0 ? (char *)dp2_pool + P.hotOff[w] : nullptr;
+			dp2_unit_pick(co, g, sv, units[ui], arena, arenaBytes, hot, (size_t)P.hotBytes[w], txArena, n_tx + ui, dbg ? dbg + 8 * (long long)ui : nullptr);
+			if (co.lane == 0 && n_tx[ui] < 0) atomic_add(overflow, 1);
+		}
+	}
+}
+#endif
+
 __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const DpUnit *units, const int *compList, int nComp,
                                                   const int *n_tx, const char *txArena, char *scratch, const long long *scr_off,
                                                   int *counter, int width)
@@ -266,6 +301,15 @@ int psc_solve(psc_ctx *ctx)
 		hostT0[who] = t;
 	};
 	CK(cudaStreamSynchronize(ctx->stream)); // uploads and the constraint build ran on the context's primary stream
+	if (!getenv("PSC_MEM_BUDGET_MB")) {
+		// scratch budget per buffer class, from what is free NOW (reads and tables are resident): up to five such
+		// buffers are alive at a time (unit scratch of the two chains, DP arenas of the two chains, transcript lists)
+		size_t fr = 0, tot = 0;
+		if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+			size_t held = st.ub[0].scratch.bytes + st.ub[1].scratch.bytes + st.db[0].dp_arena.bytes + st.db[1].dp_arena.bytes; // reusable
+			ctx->mem_budget = std::max<size_t>((size_t)256 << 20, (fr + held) / 5);
+		}
+	}
 	CK(cudaEventRecord(ctx->ev0, ctx->sMain));
 	st.reset();
 	st.h_at_cnt.assign((size_t)nc, 0); st.h_use_dp.assign((size_t)nc, 0); st.h_n_cand.assign((size_t)nc, 0);
@@ -702,6 +746,47 @@ int psc_solve(psc_ctx *ctx)
 		}
 		return 0;
 	};
+	// second attempt of the units that outgrew their arena: the program engine again, one roomy arena per group
+	// (four times the keys, 24 frames per key), in sub-chunks that fit the budget.  Returns the units still overflowing.
+	auto dp_program_retry = [&](DpPending &pd, std::vector<int> &redo, cudaStream_t strm, DpBufs &db, int *cnt) -> int {
+		std::vector<int> still;
+		size_t k0 = 0;
+		const int groupsPerBlock = 128 / ctx->coop;
+		while (k0 < redo.size()) {
+			size_t arenaR = 0, k1 = k0;
+			while (k1 < redo.size()) {
+				const DpUnit &u = pd.units[(size_t)redo[k1]];
+				int n = ctx->h_comp_off[(size_t)u.comp + 1] - ctx->h_comp_off[(size_t)u.comp];
+				int C = ctx->samples[(size_t)u.sample].h_ncon[(size_t)u.comp];
+				long long keys = std::min<long long>(4LL * dp2_wanted_keys(n), 262144);
+				size_t need = dp2_layout(nullptr, nullptr, nullptr, 0, nullptr, 0, n, ctx->h_next_cnt[(size_t)u.comp], std::max(C, 100), (int)keys, DP2_FR_PER_KEY_ROOMY);
+				need = (need + 255) & ~(size_t)255;
+				size_t a2 = std::max(arenaR, need);
+				if (k1 > k0 && a2 * (k1 - k0 + 1) > ctx->mem_budget) break;
+				arenaR = a2;
+				++k1;
+			}
+			const int nR = (int)(k1 - k0);
+			std::vector<int> sub(redo.begin() + (long)k0, redo.begin() + (long)k1);
+			const int blocksR = (nR + groupsPerBlock - 1) / groupsPerBlock;
+			if (!db.dp_arena.ensure((size_t)blocksR * groupsPerBlock * arenaR + 16) || !upload(ctx, db.dp_order, sub.data(), sub.size(), strm))
+				return ctx->fail("out of device memory (DP program arenas, second attempt)");
+			CK(cudaMemsetAsync(cnt, 0, 32, strm));
+			CK(cudaMemsetAsync(db.dp_ovf.p, 0, 64, strm));
+			KLAUNCH_ON(strm, 10, k_dp2_units, blocksR, 128, ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nR, (char *)db.dp_arena.p, arenaR,
+			           (size_t)0, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt, db.dp_ovf.as<int>(), ctx->coop, (long long *)nullptr, 1);
+			++launches;
+			CK(cudaGetLastError());
+			std::vector<int> hn((size_t)pd.units.size());
+			CK(cudaMemcpyAsync(hn.data(), db.dp_ntx.p, sizeof(int) * hn.size(), cudaMemcpyDeviceToHost, strm));
+			CK(cudaStreamSynchronize(strm));
+			for (int u : sub)
+				if (hn[(size_t)u] < 0) still.push_back(u);
+			k0 = k1;
+		}
+		redo.swap(still);
+		return 0;
+	};
 	auto dp_finish = [&](DpPending &pd, cudaStream_t strm, DpBufs &db, int *cnt) -> int {
 		if (!pd.active) return 0;
 		pd.active = false;
@@ -720,7 +805,11 @@ int psc_solve(psc_ctx *ctx)
 			if (dpDbg) {
 				CK(cudaMemsetAsync(st.dp_dbg.p, 0, sizeof(long long) * 8 * (size_t)(nUnits + 1), strm));
 			}
-			if (dp_walk_units(pd, redo, strm, db, cnt) != 0) return 1;
+			if (useV2 && !getenv("PSC_DP_NO_RETRY")) {
+				if (dp_program_retry(pd, redo, strm, db, cnt) != 0) return 1;
+				lap("dp program kernel, roomy second attempt");
+			}
+			if (!redo.empty() && dp_walk_units(pd, redo, strm, db, cnt) != 0) return 1;
 			lap("dp walk kernel (overflowed units)");
 			if (dpDbg) dp_print(pd.units, strm, "walk");
 		}
@@ -875,6 +964,35 @@ int psc_solve(psc_ctx *ctx)
 			}
 			const long long groupsPerBlock = threads / ctx->coop;
 			const int nBulk = nUnits - nCrit - nT1;
+			// packets of the bulk part (PSC_DP_PACKETS=0: fixed 16 KB slices instead)
+			std::vector<DpPacket> packets;
+			const size_t poolBytes = 72 << 10; // three blocks per SM
+			const bool usePackets = ctx->coop == 32 && useV2 && nBulk > 0 && !(getenv("PSC_DP_PACKETS") && atoi(getenv("PSC_DP_PACKETS")) == 0);
+			if (usePackets) {
+				DpPacket cur;
+				int cnt = 0;
+				size_t used = 0;
+				auto flush = [&]() {
+					if (cnt == 0) return;
+					for (int q = cnt; q < 4; ++q) { cur.unit[q] = -1; cur.hotOff[q] = 0; cur.hotBytes[q] = 0; }
+					packets.push_back(cur);
+					cnt = 0;
+					used = 0;
+				};
+				for (int k = nCrit; k < nCrit + nBulk; ++k) {
+					const int u = order[(size_t)k];
+					const int c = pd.units[(size_t)u].comp;
+					size_t need = dp2_smem_slice(ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c]);
+					if (need > poolBytes) need = 0; // runs in its global arena
+					if (cnt == 4 || used + need > poolBytes) flush();
+					cur.unit[cnt] = u;
+					cur.hotOff[cnt] = (int)used;
+					cur.hotBytes[cnt] = (int)need;
+					used += need;
+					++cnt;
+				}
+				flush();
+			}
 			long long blocks = (nBulk + groupsPerBlock - 1) / groupsPerBlock;
 			{
 				long long blocksPerSm = PSC_DP2_MINBLOCKS;
@@ -895,7 +1013,8 @@ int psc_solve(psc_ctx *ctx)
 				return ctx->fail("out of device memory (DP program arenas)");
 			CK(cudaMemsetAsync(db.dp_ntx.p, useV2 ? 0 : 0xff, sizeof(int) * (size_t)(nUnits + 1), strm));
 			CK(cudaMemsetAsync(db.dp_ovf.p, 0, 64, strm));
-			if (!upload(ctx, db.dp_units, pd.units.data(), pd.units.size(), strm) || !upload(ctx, db.dp_order, order.data(), order.size(), strm))
+			if (!upload(ctx, db.dp_units, pd.units.data(), pd.units.size(), strm) || !upload(ctx, db.dp_order, order.data(), order.size(), strm) ||
+			    (usePackets && !upload(ctx, db.dp_packets, packets.data(), packets.size(), strm)))
 				return ctx->fail("out of device memory");
 			lap("dp host prep");
 			CK(cudaMemsetAsync(cnt, 0, 32, strm));
@@ -932,7 +1051,15 @@ int psc_solve(psc_ctx *ctx)
 					CK(cudaEventRecord(ctx->evT1Done, ctx->sThird));
 					++launches;
 				}
-				if (nBulk > 0) {
+				if (usePackets) {
+					CK(cudaFuncSetAttribute(k_dp2_packets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poolBytes));
+					long long pblocks = std::min<long long>((long long)packets.size(), blocks);
+					ctx->ktime_begin(10, strm);
+					k_dp2_packets<<<(int)pblocks, 128, poolBytes, strm>>>(ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_packets.as<DpPacket>(), (int)packets.size(),
+					                                                   (char *)db.dp_arena.p, arenaBytes, (char *)db.dp_tx.p, db.dp_ntx.as<int>(), cnt,
+					                                                   db.dp_ovf.as<int>(), dbgPtr);
+					ctx->ktime_end();
+				} else if (nBulk > 0) {
 					ctx->ktime_begin(10, strm);
 					k_dp2_units<<<(int)blocks, threads, hotBytes * (size_t)(threads / 32), strm>>>(
 					    ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>() + nCrit, nBulk, (char *)db.dp_arena.p, arenaBytes, hotBytes,

@@ -17,11 +17,11 @@ struct UnitBufs {
 
 // device buffers of one DP launch sequence (k_dp_units + k_dp_merge)
 struct DpBufs {
-	DevBuf list, dp_scr_off, dp_order, dp_tx, dp_ntx, dp_units, dp_arena, dp_ovf, dp_merge_scr;
+	DevBuf list, dp_scr_off, dp_order, dp_tx, dp_ntx, dp_units, dp_arena, dp_ovf, dp_merge_scr, dp_packets;
 	DevBuf *scratch = nullptr;
 	void release()
 	{
-		DevBuf *all[] = {&list, &dp_scr_off, &dp_order, &dp_tx, &dp_ntx, &dp_units, &dp_arena, &dp_ovf, &dp_merge_scr};
+		DevBuf *all[] = {&list, &dp_scr_off, &dp_order, &dp_tx, &dp_ntx, &dp_units, &dp_arena, &dp_ovf, &dp_merge_scr, &dp_packets};
 		for (DevBuf *b : all) b->release();
 	}
 };
