@@ -452,14 +452,13 @@ def main():
         achieved = (alg / 1e9) / (per_launch_ms / 1e3) if per_launch_ms > 0 and alg > 0 else 0.0
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: read from the JSON that
         # tools/gpu/ncu_traffic.py wrote from an `ncu --set full` capture of this workload (profiles/), else null
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            ent = tj.get("k_" + names[dom])
-            if ent and not a.genes:
-                traffic = float(ent["dram_bytes_per_launch"])
-        except Exception:
-            traffic = None
+        def traffic_of(kernel):
+            try:
+                ent = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+                return float(ent["dram_bytes_per_launch"]) if ent and not a.genes else None
+            except Exception:
+                return None
+        traffic = traffic_of("k_" + names[dom])
         line = {
             "metric": METRIC, "value": total_components * a.steps / wall_max, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * wall_max / a.steps,
@@ -472,6 +471,12 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "ms_per_launch": per_launch_ms},
+            # the one streaming kernel of the path (alignment records in, constraint tables out), reported beside the
+            # dominant (latency-bound) kernel: algorithmic bytes of the step / its launch time / the measured HBM peak
+            "roofline_streaming": (lambda ms, by: {"bound": "hbm", "kernel": "k_build_constraints", "achieved": (by / 1e9) / (ms / 1e3) if ms > 0 else 0.0,
+                                                     "peak": peak, "unit": "GB/s", "frac": ((by / 1e9) / (ms / 1e3) / peak) if ms > 0 and peak else None,
+                                                     "traffic": traffic_of("k_build_constraints"), "algorithmic_bytes_per_launch": by,
+                                                     "ms_per_launch": ms})(kms[1] / max(1, kcnt[1]), float(kbytes[1])),
             "kernel_ms_per_step": {names[k]: kms[k] / a.steps for k in range(12) if kcnt[k]},
             "device_ms_per_step": dev_ms / a.steps,
             "components_per_rank": ncomp, "transcripts_per_rank": int(ntx),

@@ -840,42 +840,61 @@ PSC_DEV int dp_augment(DpState &st, uint64_t *cb, int *cf, int *cl, int A, int l
 	int size = A;
 	bool full = false;
 	co.sync();
-	if (co.lane == 0) {
-		for (int i = 0; i < size && !full; ++i) {
+	// The reference appends, row by row, the suffixes that start at a possible start and then the prefixes that end
+	// at a possible end, and stops the moment `limit` rows exist.  Same rows in the same order here, but counted per
+	// source row first (lanes over rows), placed by a running offset, and cut at the limit.
+	const int room = limit - A; // > 0
+	int base = 0;               // rows appended by the source rows before the current batch
+	for (int b0 = 0; b0 < size && base < room; b0 += co.n) {
+		const int i = b0 + co.lane;
+		int nSuf = 0, nPre = 0;
+		if (i < size) {
 			const uint64_t *src = cb + (long long)i * W;
-			int tf = cf[i], tl = cl[i];
-			// suffixes starting at a possible start
-			bool firstSeen = false;
-			for (int q = tf; q <= tl && !full; ++q) {
-				if (!bt_test(src, q)) continue;
-				if (!firstSeen) { firstSeen = true; continue; }
-				if (st.cs[q]) {
-					if (A >= cap) { *st.err = 24; full = true; break; }
-					uint64_t *dst = cb + (long long)A * W;
-					for (int w = 0; w < W; ++w) dst[w] = src[w] & keep_mask(w, q, tl);
-					cf[A] = q;
-					cl[A] = tl;
-					++A;
-					if (A >= limit) full = true;
-				}
-			}
-			// prefixes ending at a possible end
-			for (int q = tf; q < tl && !full; ++q) {
-				if (!bt_test(src, q)) continue;
-				if (st.ce[q]) {
-					if (A >= cap) { *st.err = 24; full = true; break; }
-					uint64_t *dst = cb + (long long)A * W;
-					for (int w = 0; w < W; ++w) dst[w] = src[w] & keep_mask(w, tf, q);
-					cf[A] = tf;
-					cl[A] = q;
-					++A;
-					if (A >= limit) full = true;
-				}
-			}
+			const int tf = cf[i], tl = cl[i];
+			for (int q = tf + 1; q <= tl; ++q)
+				if (bt_test(src, q) && st.cs[q]) ++nSuf; // bit tf is the first set bit: suffixes start at later ones
+			for (int q = tf; q < tl; ++q)
+				if (bt_test(src, q) && st.ce[q]) ++nPre;
 		}
+		const int mine = nSuf + nPre;
+		// exclusive prefix over the lanes of this batch
+		int off = 0, tot = 0;
+		for (int l = 0; l < co.n; ++l) {
+			int v = co.bcast(mine, l);
+			if (l < co.lane) off += v;
+			tot += v;
+		}
+		if (i < size && mine > 0) {
+			const uint64_t *src = cb + (long long)i * W;
+			const int tf = cf[i], tl = cl[i];
+			int k = base + off; // index among the appended rows
+			for (int q = tf + 1; q <= tl && k < room; ++q)
+				if (bt_test(src, q) && st.cs[q]) {
+					if ((long long)A + k >= cap) { *st.err = 24; break; }
+					uint64_t *dst = cb + (long long)(A + k) * W;
+					for (int w = 0; w < W; ++w) dst[w] = src[w] & keep_mask(w, q, tl);
+					cf[A + k] = q;
+					cl[A + k] = tl;
+					++k;
+				}
+			for (int q = tf; q < tl && k < room; ++q)
+				if (bt_test(src, q) && st.ce[q]) {
+					if ((long long)A + k >= cap) { *st.err = 24; break; }
+					uint64_t *dst = cb + (long long)(A + k) * W;
+					for (int w = 0; w < W; ++w) dst[w] = src[w] & keep_mask(w, tf, q);
+					cf[A + k] = tf;
+					cl[A + k] = q;
+					++k;
+				}
+		}
+		base += tot;
 	}
-	A = co.bcast(A, 0);
-	full = co.bcast((int)full, 0) != 0;
+	if (base >= room) {
+		base = room;
+		full = true;
+	}
+	A += base;
+	if ((long long)A > cap) A = (int)cap;
 	co.sync();
 	if (full) return A; // the reference returns before the final coalesce when the limit is hit
 	return dp_coalesce(st, cb, cf, cl, A);

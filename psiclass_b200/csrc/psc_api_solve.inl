@@ -1192,6 +1192,7 @@ int psc_solve(psc_ctx *ctx)
 		ctx->timing.kernel_bytes[5] = bytes;
 		ctx->timing.kernel_bytes[8] = bytes;
 		ctx->timing.kernel_bytes[4] = dpBytes;
+		ctx->timing.kernel_bytes[10] = dpBytes; // the static-program engine reads / writes the same tables
 	}
 	ctx->timing.solve_ms = ms;
 	ctx->timing.kernel_launches += launches;
