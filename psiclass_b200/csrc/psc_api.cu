@@ -170,7 +170,7 @@ struct psc_ctx {
 	// few critical (component, sample) units whose single-warp latency chains set the step time (they then run one
 	// warp per SM sub-partition, undisturbed) and the rest for everything else: sMain / sSecond live in the big
 	// partition, sCrit in the small one.  Otherwise these are ordinary streams (sMain == stream, sSecond == stream2).
-	cudaStream_t sMain = 0, sSecond = 0, sCrit = 0, sThird = 0; // sThird: the one-thread-per-unit DP launch of the bulk
+	cudaStream_t sMain = 0, sSecond = 0, sCrit = 0, sThird = 0; // sThird: the chain of the enumerated components
 	cudaEvent_t evCritGo = 0, evCritDone = 0, evT1Go = 0, evT1Done = 0;
 	int critSms = 0; // SMs of the critical partition, 0: no partitioning
 #ifndef PSC_CPU_SHIM
@@ -662,9 +662,9 @@ int psc_build_constraints(psc_ctx *ctx)
 	std::vector<SampleDev> hs((size_t)S);
 	for (int si = 0; si < S; ++si) hs[(size_t)si] = ctx->samples[(size_t)si].d;
 	if (!upload(ctx, ctx->d_samples, hs.data(), (size_t)S) || !upload(ctx, ctx->d_order, order.data(), (size_t)nUnits) ||
-	    !ctx->d_counter.ensure(64))
+	    !ctx->d_counter.ensure(256))
 		return ctx->fail("out of device memory");
-	CK(cudaMemsetAsync(ctx->d_counter.p, 0, 64, ctx->stream));
+	CK(cudaMemsetAsync(ctx->d_counter.p, 0, 256, ctx->stream));
 	if (nUnits > 0) {
 		int block = 128;
 		int grid = ctx->n_sm * 16;

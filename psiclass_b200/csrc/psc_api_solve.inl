@@ -291,14 +291,19 @@ int psc_solve(psc_ctx *ctx)
 	const bool hostDbg = getenv("PSC_DEBUG_HOST") != nullptr;
 	const auto solveT0 = std::chrono::steady_clock::now();
 	const std::thread::id mainThread = std::this_thread::get_id();
-	std::chrono::steady_clock::time_point hostT0[2] = {solveT0, solveT0}; // [1]: the helper thread of the second stream
+	std::mutex lapMu;
+	std::vector<std::pair<std::thread::id, std::chrono::steady_clock::time_point>> lapT0; // per host thread
 	auto lap = [&](const char *what) {
 		if (!hostDbg) return;
-		const int who = std::this_thread::get_id() == mainThread ? 0 : 1;
+		std::lock_guard<std::mutex> lk(lapMu);
+		const std::thread::id me = std::this_thread::get_id();
+		size_t who = 0;
+		while (who < lapT0.size() && lapT0[who].first != me) ++who;
+		if (who == lapT0.size()) lapT0.push_back({me, solveT0});
 		auto t = std::chrono::steady_clock::now();
-		fprintf(stderr, "[host%s] %-28s %8.2f ms  (at %8.2f)\n", who ? " 2" : "", what, std::chrono::duration<double, std::milli>(t - hostT0[who]).count(),
-		        std::chrono::duration<double, std::milli>(t - solveT0).count());
-		hostT0[who] = t;
+		fprintf(stderr, "[host%s] %-28s %8.2f ms  (at %8.2f)\n", me == mainThread ? "" : (who == 1 ? " 2" : " 3"), what,
+		        std::chrono::duration<double, std::milli>(t - lapT0[who].second).count(), std::chrono::duration<double, std::milli>(t - solveT0).count());
+		lapT0[who].second = t;
 	};
 	CK(cudaStreamSynchronize(ctx->stream)); // uploads and the constraint build ran on the context's primary stream
 	if (!getenv("PSC_MEM_BUDGET_MB")) {
@@ -427,14 +432,19 @@ int psc_solve(psc_ctx *ctx)
 	// ---- P3..P6 per chunk of components, as a pass over all components (pass 0), over all but the heavy DP
 	// components (1) or over the heavy DP components (2).  Pass 1 runs on the second stream with its own buffers
 	// while the heavy DP units are still busy on the main one. ----
-	std::vector<char> group((size_t)nc, 0); // 2: heavy DP component
+	std::vector<char> group((size_t)nc, 0); // 0: enumerated component, 1: DP component of the bulk, 2: heavy DP component
+	// pass 0: every component; 1: everything but the heavy ones; 2: the heavy ones; 3: the enumerated ones; 4: the bulk DP ones
+	auto in_pass = [&](int pass, int c) {
+		const int gr = group[(size_t)c];
+		return pass == 0 || (pass == 1 && gr != 2) || (pass == 2 && gr == 2) || (pass == 3 && gr == 0) || (pass == 4 && gr == 1);
+	};
 	auto run_units = [&](int pass, cudaStream_t strm, UnitBufs &ub, int *cnt, ResultSet &R) -> int {
 		// per (component, sample) scratch needs of this pass, computed on a few host threads
 		std::vector<long long> soAll((size_t)nc * S, 0), poAll((size_t)nc * S, 0), sNeedAll((size_t)nc, 0), pNeedAll((size_t)nc, 0);
 		{
 			auto work = [&](int ca, int cb) {
 				for (int c = ca; c < cb; ++c) {
-					const bool mine = pass == 0 || (group[(size_t)c] == 2) == (pass == 2);
+					const bool mine = in_pass(pass, c);
 					if (!mine) continue;
 					int n = ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c];
 					int A = st.h_n_cand[(size_t)c];
@@ -468,7 +478,7 @@ int psc_solve(psc_ctx *ctx)
 				int A = st.h_n_cand[(size_t)c1];
 				const long long sNeed = sNeedAll[(size_t)c1], pNeed = pNeedAll[(size_t)c1];
 				const long long *so = &soAll[(size_t)c1 * S], *po = &poAll[(size_t)c1 * S];
-				const bool mine = pass == 0 || (group[(size_t)c1] == 2) == (pass == 2);
+				const bool mine = in_pass(pass, c1);
 				if (c1 > c0 && (size_t)(sAcc + sNeed) > ctx->mem_budget) break;
 				for (int s = 0; s < S; ++s) {
 					scrOff.push_back(sAcc + so[(size_t)s]);
@@ -1112,6 +1122,7 @@ int psc_solve(psc_ctx *ctx)
 			for (size_t k = 0; k < nH; ++k) isH[(size_t)byC[k].second] = 1;
 			for (int c : dpList) (isH[(size_t)c] ? heavy : rest).push_back(c);
 			for (int c : heavy) group[(size_t)c] = 2;
+			for (int c : rest) group[(size_t)c] = 1;
 		}
 	}
 	// n_cand of the components of `comps`, copied from the device on `strm` (the two chains own disjoint components)
@@ -1131,21 +1142,31 @@ int psc_solve(psc_ctx *ctx)
 		const cudaStream_t sHeavy = ctx->critSms > 0 ? ctx->sCrit : ctx->sMain;
 		if (dp_launch(heavy, sHeavy, st.db[0], counter, pdH, true) != 0) return 1;
 		if (dp_launch(rest, ctx->sSecond, st.db[1], counter + 8, pdR, false) != 0) return 1;
-		ResultSet &resR = st.passR, &resH = st.passH;
+		ResultSet &resR = st.passR, &resH = st.passH, &resE = st.passE;
 		resR.reset();
 		resH.reset();
-		int rcR = 0;
+		resE.reset();
+		// A third chain: the enumerated components need no DP, so their set cover / EM / emit start right away on a
+		// stream of their own and fill the SMs the (latency-bound) DP launches leave idle (PSC_THREE_CHAINS=0: off)
+		const bool three = !(getenv("PSC_THREE_CHAINS") && atoi(getenv("PSC_THREE_CHAINS")) == 0);
+		int rcR = 0, rcE = 0;
 		std::thread second([&]() {
 			cudaSetDevice(ctx->device);
 			rcR = [&]() -> int {
 				if (dp_finish(pdR, ctx->sSecond, st.db[1], counter + 8) != 0) return 1;
 				if (fetch_n_cand(rest, ctx->sSecond) != 0) return 1;
 				lap("dp merge (second stream)");
-				if (run_units(1, ctx->sSecond, st.ub[1], counter + 8, resR) != 0) return 1;
+				if (run_units(three ? 4 : 1, ctx->sSecond, st.ub[1], counter + 8, resR) != 0) return 1;
 				lap("second stream done");
 				return 0;
 			}();
 		});
+		std::thread third;
+		if (three)
+			third = std::thread([&]() {
+				cudaSetDevice(ctx->device);
+				rcE = run_units(3, ctx->sThird, st.ub[2], counter + 16, resE);
+			});
 		int rcH = [&]() -> int {
 			if (dp_finish(pdH, sHeavy, st.db[0], counter) != 0) return 1;
 			if (fetch_n_cand(heavy, sHeavy) != 0) return 1;
@@ -1153,8 +1174,13 @@ int psc_solve(psc_ctx *ctx)
 			return run_units(2, sHeavy, st.ub[0], counter, resH);
 		}();
 		second.join();
-		if (rcH != 0 || rcR != 0) return 1;
-		lap("both chains done");
+		if (third.joinable()) third.join();
+		if (rcH != 0 || rcR != 0 || rcE != 0) return 1;
+		lap("all chains done");
+		if (three) {
+			merge_passes(st.passRE, resE, resR);
+			merge_passes(st, st.passRE, resH);
+		} else
 		merge_passes(st, resR, resH);
 	} else {
 		if (!dpList.empty()) {

@@ -43,7 +43,7 @@ struct SolveState : ResultSet {
 	DevBuf can_start, can_end, edge_support, cs00, at_cnt, use_dp, def_gene, n_cand, cand_row_off, cand_bits_off,
 	    cand_bits, cand_first, cand_last, cand_corr, cand_sup1, cand_sup2, error_flag, fscratch, fs_off, list, stk, dp_dbg,
 	    dp_heavy_scratch, dp_rest_scratch;
-	UnitBufs ub[2];
+	UnitBufs ub[3]; // heavy chain, bulk DP chain, enumerated-components chain
 	// db[0]: the heavy DP components; db[1]: the others.  The scratch buffers are only used by the walk-engine fallback.
 	DpBufs db[2];
 	SolveState()
@@ -52,7 +52,7 @@ struct SolveState : ResultSet {
 		db[1].scratch = &dp_rest_scratch;
 	}
 	std::vector<int> h_at_cnt, h_use_dp, h_n_cand;
-	ResultSet passR, passH; // per-pass results (kept across calls: no reallocation, no page faults after the first step)
+	ResultSet passR, passH, passE, passRE; // per-pass results (kept across calls: no reallocation, no page faults after the first step)
 	// results, host side (filled chunk by chunk): the ResultSet base
 	void release()
 	{
@@ -62,6 +62,7 @@ struct SolveState : ResultSet {
 		for (DevBuf *b : all) b->release();
 		ub[0].release();
 		ub[1].release();
+		ub[2].release();
 		db[0].release();
 		db[1].release();
 	}
