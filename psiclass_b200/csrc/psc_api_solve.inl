@@ -1146,9 +1146,11 @@ int psc_solve(psc_ctx *ctx)
 		resR.reset();
 		resH.reset();
 		resE.reset();
-		// A third chain: the enumerated components need no DP, so their set cover / EM / emit start right away on a
-		// stream of their own and fill the SMs the (latency-bound) DP launches leave idle (PSC_THREE_CHAINS=0: off)
-		const bool three = !(getenv("PSC_THREE_CHAINS") && atoi(getenv("PSC_THREE_CHAINS")) == 0);
+		// A third chain (PSC_THREE_CHAINS=1): the enumerated components need no DP, so their set cover / EM / emit can
+		// start right away on a stream of their own.  Off by default -- measured on B200 it does not pay: the DP launch's
+		// resident blocks hold the whole register file (3 x 128 threads x 168 registers), so the chain's blocks only
+		// get onto the SMs when the DP blocks retire, and they then delay the merge kernels (708 vs 665 ms per step).
+		const bool three = getenv("PSC_THREE_CHAINS") && atoi(getenv("PSC_THREE_CHAINS")) != 0;
 		int rcR = 0, rcE = 0;
 		std::thread second([&]() {
 			cudaSetDevice(ctx->device);
