@@ -934,6 +934,7 @@ int psc_solve(psc_ctx *ctx)
 			const int threads = 128;
 			size_t hotBytes = 0, hotCrit = 0;
 			int nCrit = 0;
+			bool critOnThird = false;
 			if (ctx->coop == 32) {
 				hotBytes = std::min<size_t>((hotWanted + 1023) & ~(size_t)1023, 16 << 10);
 				if (const char *e = getenv("PSC_DP_SMEM_KB")) hotBytes = (size_t)std::max(0, atoi(e)) << 10;
@@ -942,11 +943,20 @@ int psc_solve(psc_ctx *ctx)
 					if (const char *e = getenv("PSC_DP_CRIT")) nCrit = std::max(0, atoi(e));
 					nCrit = std::min(nCrit, nUnits / 2);
 					if (strm == ctx->sCrit) nCrit = nUnits; // the launch already lives in the critical partition: every unit takes that shape
+				} else if (!heavyLaunch && useV2 && !dpDbg && nUnits >= 4096) {
+					// the bulk launch's own tail: its most expensive units -- one per SM of the partition -- also run one per
+					// block with a big slice, next to two (instead of three) regular blocks per SM (PSC_DP_CRIT_BULK)
+					nCrit = ctx->n_sm - ctx->critSms;
+					if (const char *e = getenv("PSC_DP_CRIT_BULK")) nCrit = std::max(0, atoi(e));
+					nCrit = std::min(nCrit, nUnits / 8);
+					critOnThird = nCrit > 0;
+				}
+				if (nCrit > 0) {
 					for (int k = 0; k < nCrit; ++k) {
 						int c = pd.units[(size_t)order[(size_t)k]].comp;
 						hotCrit = std::max(hotCrit, dp2_smem_wanted(ctx->h_comp_off[(size_t)c + 1] - ctx->h_comp_off[(size_t)c]));
 					}
-					hotCrit = std::min<size_t>((hotCrit + 1023) & ~(size_t)1023, 110 << 10);
+					hotCrit = std::min<size_t>((hotCrit + 1023) & ~(size_t)1023, critOnThird ? (92 << 10) : (110 << 10));
 				}
 			}
 			// The bulk launch hands the light end of its list to a one-thread-per-unit launch: the interpreter is scalar per
@@ -1005,7 +1015,7 @@ int psc_solve(psc_ctx *ctx)
 			}
 			long long blocks = (nBulk + groupsPerBlock - 1) / groupsPerBlock;
 			{
-				long long blocksPerSm = PSC_DP2_MINBLOCKS;
+				long long blocksPerSm = critOnThird ? 2 : PSC_DP2_MINBLOCKS;
 				if (hotBytes > 0) blocksPerSm = std::max<long long>(1, std::min<long long>(blocksPerSm, (long long)((227 << 10) / (hotBytes * 4 + 1024))));
 				blocks = std::min<long long>(blocks, (long long)ctx->n_sm * blocksPerSm);
 				long long fit = (long long)(ctx->mem_budget / (arenaBytes * (size_t)groupsPerBlock));
@@ -1041,13 +1051,14 @@ int psc_solve(psc_ctx *ctx)
 				if (nCrit > 0) {
 					// the critical units: the setup above must be visible to their stream, and the merge waits for them
 					CK(cudaEventRecord(ctx->evCritGo, strm));
-					CK(cudaStreamWaitEvent(ctx->sCrit, ctx->evCritGo, 0));
-					ctx->ktime_begin(10, ctx->sCrit);
-					k_dp2_units<<<nCrit, 32, hotCrit, ctx->sCrit>>>(ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nCrit,
+					const cudaStream_t sC = critOnThird ? ctx->sThird : ctx->sCrit;
+					CK(cudaStreamWaitEvent(sC, ctx->evCritGo, 0));
+					ctx->ktime_begin(10, sC);
+					k_dp2_units<<<nCrit, 32, hotCrit, sC>>>(ctx->gd, sv, db.dp_units.as<DpUnit>(), db.dp_order.as<int>(), nCrit,
 					                                              (char *)db.dp_arena.p + bulkArenas * arenaBytes, arenaBytes, hotCrit, (char *)db.dp_tx.p,
 					                                              db.dp_ntx.as<int>(), cnt + 4, db.dp_ovf.as<int>(), ctx->coop, dbgPtr);
 					ctx->ktime_end();
-					CK(cudaEventRecord(ctx->evCritDone, ctx->sCrit));
+					CK(cudaEventRecord(ctx->evCritDone, sC));
 					++launches;
 				}
 				if (nT1 > 0) {
