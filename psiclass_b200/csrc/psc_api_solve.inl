@@ -944,9 +944,10 @@ int psc_solve(psc_ctx *ctx)
 					nCrit = std::min(nCrit, nUnits / 2);
 					if (strm == ctx->sCrit) nCrit = nUnits; // the launch already lives in the critical partition: every unit takes that shape
 				} else if (!heavyLaunch && useV2 && !dpDbg && nUnits >= 4096) {
-					// the bulk launch's own tail: its most expensive units -- one per SM of the partition -- also run one per
-					// block with a big slice, next to two (instead of three) regular blocks per SM (PSC_DP_CRIT_BULK)
-					nCrit = ctx->n_sm - ctx->critSms;
+					// the bulk launch's own tail (PSC_DP_CRIT_BULK=<n units>, off by default): its most expensive units can also
+					// run one per block with a big slice, next to two (instead of three) regular blocks per SM.  Measured on
+					// B200: the launch gets slower (321 vs 268 ms), the lost third of the regular blocks costs more.
+					nCrit = 0;
 					if (const char *e = getenv("PSC_DP_CRIT_BULK")) nCrit = std::max(0, atoi(e));
 					nCrit = std::min(nCrit, nUnits / 8);
 					critOnThird = nCrit > 0;
