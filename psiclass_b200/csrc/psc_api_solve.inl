@@ -147,9 +147,11 @@ __global__ void __launch_bounds__(128) k_dp_merge(GraphDev g, SolveDev sv, const
 	uint64_t *sort64 = nullptr;
 	int sort64Cap = 0;
 #ifndef PSC_CPU_SHIM
-	extern __shared__ __align__(16) uint64_t merge_smem[]; // 4 * PSC_MERGE_SORT_CAP words (dynamic: 64 KB)
+	// one warp per block and 16 KB of static shared memory: a kernel asking for 64 KB per block had to wait for SMs
+	// to drain of the other chain's (shared-memory-free) kernels before it could start
+	__shared__ __align__(16) uint64_t merge_smem[PSC_MERGE_SORT_CAP];
 	if (width == 32) {
-		sort64 = merge_smem + (threadIdx.x >> 5) * PSC_MERGE_SORT_CAP;
+		sort64 = merge_smem;
 		sort64Cap = PSC_MERGE_SORT_CAP;
 	}
 #else
@@ -829,11 +831,12 @@ int psc_solve(psc_ctx *ctx)
 		CK(cudaMemsetAsync(cnt, 0, 32, strm));
 #ifndef PSC_CPU_SHIM
 		{
-			const size_t smemBytes = ctx->coop == 32 ? 4 * PSC_MERGE_SORT_CAP * sizeof(uint64_t) : 0;
-			CK(cudaFuncSetAttribute(k_dp_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PSC_MERGE_SORT_CAP * (int)sizeof(uint64_t)));
+			// coop 32: one warp (= one component at a time) per block; coop 1: 128 one-thread groups per block
+			const int mThreads = ctx->coop == 32 ? 32 : 128;
+			const int mBlocks = ctx->coop == 32 ? std::max(1, std::min(pd.nComp, ctx->n_sm * 12)) : launch_grid(ctx, pd.nComp);
 			std::lock_guard<std::mutex> lk_(ctx->launchMu);
 			ctx->ktime_begin(7, strm);
-			k_dp_merge<<<launch_grid(ctx, pd.nComp), 128, smemBytes, strm>>>(ctx->gd, sv, db.dp_units.as<DpUnit>(), db.list.as<int>(), pd.nComp,
+			k_dp_merge<<<mBlocks, mThreads, 0, strm>>>(ctx->gd, sv, db.dp_units.as<DpUnit>(), db.list.as<int>(), pd.nComp,
 			                                                                 db.dp_ntx.as<int>(), (const char *)db.dp_tx.p, (char *)db.dp_merge_scr.p,
 			                                                                 db.dp_scr_off.as<long long>(), cnt, ctx->coop);
 			ctx->ktime_end();
