@@ -273,6 +273,7 @@ int main(int argc, char *argv[])
 	int S = (int)bamPaths.size();
 	if (numThreads < 1) numThreads = 1;
 	const double tStart = now_s();
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); // psc_solve drives several streams at once (before CUDA initialises)
 	int nGpu = 1;
 	if (const char *e = getenv("PSC_GPUS")) nGpu = std::max(1, atoi(e));
 	std::vector<EarlyCtx> early((size_t)nGpu);
