@@ -286,7 +286,15 @@ int main(int argc, char *argv[])
 		std::vector<std::string> names;
 		std::vector<int32_t> lens;
 		if (!psc::read_bam_header(bamPaths[0], names, lens, graphErr)) return;
+		// PSC_GRAPH_CACHE=1: the parsed graph is kept as <subexon file>.pscgraph and mapped back on the next run
+		const char *gc = getenv("PSC_GRAPH_CACHE");
+		const bool useCache = gc && atoi(gc) != 0;
+		if (useCache && psc::load_graph_cache(subexonPath + ".pscgraph", subexonPath, names, classifierThreshold, g)) {
+			graphOk = true;
+			return;
+		}
 		graphOk = psc::load_subexon_graph(subexonPath, names, classifierThreshold, g, graphErr);
+		if (graphOk && useCache) psc::save_graph_cache(subexonPath + ".pscgraph", subexonPath, classifierThreshold, g);
 	});
 	// ---- one decode pass per BAM (library statistics + alignment records), samples in parallel ----
 	std::vector<psc::SampleReads> samples((size_t)S);

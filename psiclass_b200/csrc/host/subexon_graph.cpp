@@ -1,6 +1,11 @@
 // See subexon_graph.h.  Every step cites the reference lines whose behaviour it reproduces.
 #include "subexon_graph.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -374,6 +379,137 @@ bool load_subexon_graph(const std::string &path, const std::vector<std::string> 
 	}
 	g.comp_off[g.n_comp] = n;
 	return true;
+}
+
+// -------------------------------------------------------------------------------------------
+// binary cache
+// -------------------------------------------------------------------------------------------
+namespace {
+const uint64_t CACHE_MAGIC = 0x3148504152474350ull; // "PCGRAPH1"
+
+bool source_stamp(const std::string &path, uint64_t &size, uint64_t &mtime)
+{
+	struct stat st;
+	if (stat(path.c_str(), &st) != 0) return false;
+	size = (uint64_t)st.st_size;
+	mtime = (uint64_t)st.st_mtime;
+	return true;
+}
+template <class T> void put_vec(std::string &out, const std::vector<T> &v)
+{
+	uint64_t n = v.size();
+	out.append((const char *)&n, 8);
+	if (n) out.append((const char *)v.data(), n * sizeof(T));
+	out.append((8 - out.size() % 8) % 8, '\0');
+}
+template <class T> bool get_vec(const char *&p, const char *end, std::vector<T> &v)
+{
+	if (end - p < 8) return false;
+	uint64_t n;
+	memcpy(&n, p, 8);
+	p += 8;
+	if ((uint64_t)(end - p) < n * sizeof(T)) return false;
+	v.resize((size_t)n);
+	if (n) memcpy(v.data(), p, (size_t)n * sizeof(T));
+	p += n * sizeof(T);
+	p += (8 - (uintptr_t)(n * sizeof(T)) % 8) % 8;
+	return p <= end;
+}
+} // namespace
+
+bool save_graph_cache(const std::string &cachePath, const std::string &sourcePath, double thr, const Graph &g)
+{
+	uint64_t size = 0, mtime = 0;
+	if (!source_stamp(sourcePath, size, mtime)) return false;
+	std::string out;
+	out.append((const char *)&CACHE_MAGIC, 8);
+	out.append((const char *)&size, 8);
+	out.append((const char *)&mtime, 8);
+	out.append((const char *)&thr, 8);
+	uint64_t nchr = g.chr_names.size();
+	out.append((const char *)&nchr, 8);
+	for (auto &c : g.chr_names) {
+		uint64_t l = c.size();
+		out.append((const char *)&l, 8);
+		out.append(c);
+		out.append((8 - out.size() % 8) % 8, '\0');
+	}
+	int64_t ncomp = g.n_comp;
+	out.append((const char *)&ncomp, 8);
+	put_vec(out, g.comp_off); put_vec(out, g.comp_chr); put_vec(out, g.comp_start); put_vec(out, g.comp_end);
+	put_vec(out, g.comp_base_gene); put_vec(out, g.comp_used_gene);
+	put_vec(out, g.se_start); put_vec(out, g.se_end); put_vec(out, g.se_left_type); put_vec(out, g.se_right_type);
+	put_vec(out, g.se_left_strand); put_vec(out, g.se_right_strand); put_vec(out, g.se_left_cls); put_vec(out, g.se_right_cls);
+	put_vec(out, g.se_gene_id); put_vec(out, g.next_off); put_vec(out, g.next_idx); put_vec(out, g.prev_off); put_vec(out, g.prev_idx);
+	std::string tmp = cachePath + ".tmp";
+	FILE *fp = fopen(tmp.c_str(), "wb");
+	if (!fp) return false;
+	bool ok = fwrite(out.data(), 1, out.size(), fp) == out.size();
+	ok = fclose(fp) == 0 && ok;
+	if (ok) ok = rename(tmp.c_str(), cachePath.c_str()) == 0; // readers never see a half-written cache
+	if (!ok) remove(tmp.c_str());
+	return ok;
+}
+
+bool load_graph_cache(const std::string &cachePath, const std::string &sourcePath, const std::vector<std::string> &chrNames, double thr,
+                      Graph &g)
+{
+	uint64_t size = 0, mtime = 0;
+	if (!source_stamp(sourcePath, size, mtime)) return false;
+	int fd = open(cachePath.c_str(), O_RDONLY);
+	if (fd < 0) return false;
+	struct stat st;
+	if (fstat(fd, &st) != 0 || st.st_size < 48) {
+		close(fd);
+		return false;
+	}
+	void *map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+	close(fd);
+	if (map == MAP_FAILED) return false;
+	const char *p = (const char *)map, *end = p + st.st_size;
+	Graph t;
+	bool ok = false;
+	do {
+		uint64_t hdr[5];
+		memcpy(hdr, p, 40);
+		p += 40;
+		double cthr;
+		memcpy(&cthr, &hdr[3], 8);
+		if (hdr[0] != CACHE_MAGIC || hdr[1] != size || hdr[2] != mtime || cthr != thr || hdr[4] != chrNames.size()) break;
+		bool same = true;
+		for (size_t k = 0; k < chrNames.size() && same; ++k) {
+			if (end - p < 8) { same = false; break; }
+			uint64_t l;
+			memcpy(&l, p, 8);
+			p += 8;
+			if ((uint64_t)(end - p) < l || l != chrNames[k].size() || memcmp(p, chrNames[k].data(), (size_t)l) != 0) { same = false; break; }
+			p += l;
+			p += (8 - (uintptr_t)(p - (const char *)map) % 8) % 8;
+		}
+		if (!same || end - p < 8) break;
+		int64_t ncomp;
+		memcpy(&ncomp, p, 8);
+		p += 8;
+		t.n_comp = (int32_t)ncomp;
+		t.chr_names = chrNames;
+		if (!(get_vec(p, end, t.comp_off) && get_vec(p, end, t.comp_chr) && get_vec(p, end, t.comp_start) && get_vec(p, end, t.comp_end) &&
+		      get_vec(p, end, t.comp_base_gene) && get_vec(p, end, t.comp_used_gene) && get_vec(p, end, t.se_start) && get_vec(p, end, t.se_end) &&
+		      get_vec(p, end, t.se_left_type) && get_vec(p, end, t.se_right_type) && get_vec(p, end, t.se_left_strand) &&
+		      get_vec(p, end, t.se_right_strand) && get_vec(p, end, t.se_left_cls) && get_vec(p, end, t.se_right_cls) &&
+		      get_vec(p, end, t.se_gene_id) && get_vec(p, end, t.next_off) && get_vec(p, end, t.next_idx) && get_vec(p, end, t.prev_off) &&
+		      get_vec(p, end, t.prev_idx)))
+			break;
+		// shape checks: a damaged file must not reach the kernels
+		size_t nse = t.se_start.size();
+		if (t.n_comp < 0 || t.comp_off.size() != (size_t)t.n_comp + 1 || t.comp_chr.size() != (size_t)t.n_comp || t.se_end.size() != nse ||
+		    t.next_off.size() != nse + 1 || t.prev_off.size() != nse + 1 || (nse && (size_t)t.comp_off.back() != nse) ||
+		    (nse && ((size_t)t.next_off.back() != t.next_idx.size() || (size_t)t.prev_off.back() != t.prev_idx.size())))
+			break;
+		ok = true;
+	} while (false);
+	munmap(map, (size_t)st.st_size);
+	if (ok) g = std::move(t);
+	return ok;
 }
 
 } // namespace psc

@@ -41,4 +41,13 @@ struct Graph {
 bool load_subexon_graph(const std::string &path, const std::vector<std::string> &chr_names,
                         double classifier_threshold, Graph &g, std::string &err);
 
+// Binary form of a parsed graph: the arrays above, little-endian, behind a header that pins the source
+// file (size, mtime), the classifier threshold and the chromosome names it was built for.  `load_graph_cache` maps the
+// file and copies the arrays out; it returns false (and leaves `g` untouched) when the file is missing, truncated or
+// was made from a different source / threshold / header.  `classes` uses `<subexon file>.pscgraph` when the
+// environment has PSC_GRAPH_CACHE=1: read it if valid, else parse the text and write it.
+bool save_graph_cache(const std::string &cache_path, const std::string &source_path, double classifier_threshold, const Graph &g);
+bool load_graph_cache(const std::string &cache_path, const std::string &source_path, const std::vector<std::string> &chr_names,
+                      double classifier_threshold, Graph &g);
+
 } // namespace psc

@@ -150,3 +150,34 @@ def test_empty_and_ragged_inputs():
     wl = testkit.Workload.synth(seed=47, n_genes=30, n_samples=3, mean_pairs=0.3, exon_min=1, exon_max=2, threads=2)
     rep = wl.check(testkit.SHIM_PATH, coop=1)
     assert rep.passed, rep.summary()
+
+
+def test_graph_cache_round_trip_and_invalidation(tmp_path):
+    """the parsed subexon graph as a binary file (<subexon file>.pscgraph, PSC_GRAPH_CACHE=1).  A valid
+    cache gives the same GTFs as parsing; a truncated one, one made for another classifier threshold or for another
+    source file is ignored."""
+    d = stage_fixture("dp_small", tmp_path)
+    env = dict(os.environ, PSC_GRAPH_CACHE="1")
+    cache = os.path.join(d, "subexon_combined.out.pscgraph")
+    n = len(open(os.path.join(d, "bamlist")).read().split())
+
+    def classes(prefix, extra=(), e=env):
+        run([CLASSES_SHIM, "--lb", "bamlist", "-s", "subexon_combined.out", "-o", prefix, "-p", "2"] + list(extra), cwd=d, env=e)
+        return [gtf_body(os.path.join(d, "%s_sample_%d.gtf" % (prefix, s))) for s in range(n)]
+
+    ref = [gtf_body(os.path.join(d, "ref_sample_%d.gtf" % s)) for s in range(n)]
+    assert classes("a") == ref and os.path.exists(cache)          # parsed, cache written
+    stamp = os.path.getmtime(cache)
+    assert classes("b") == ref and os.path.getmtime(cache) == stamp  # read back from the cache, not rewritten
+    # another threshold: the cache is for -c 0.05, so it is ignored (and replaced)
+    plain = classes("c", ["-c", "0.5"], dict(os.environ))
+    assert classes("d", ["-c", "0.5"]) == plain
+    # truncated cache: ignored
+    with open(cache, "r+b") as f:
+        f.truncate(200)
+    assert classes("e") == ref
+    # source changed after the cache was made: ignored
+    assert classes("f") == ref
+    stamp = os.path.getmtime(cache)
+    os.utime(os.path.join(d, "subexon_combined.out"), (1, 1))
+    assert classes("g") == ref and os.path.getmtime(cache) != stamp   # reparsed and rewritten for the new stamp
