@@ -382,6 +382,31 @@ bool load_subexon_graph(const std::string &path, const std::vector<std::string> 
 }
 
 // -------------------------------------------------------------------------------------------
+// text writer
+// -------------------------------------------------------------------------------------------
+bool write_subexon_file(const Graph &g, const std::string &path)
+{
+	FILE *fp = fopen(path.c_str(), "w");
+	if (!fp) return false;
+	static const char sc[] = "-.+";
+	for (int c = 0; c < g.n_comp; ++c) {
+		const int b = g.comp_off[(size_t)c], e = g.comp_off[(size_t)c + 1];
+		const char *chr = g.chr_names[(size_t)g.comp_chr[(size_t)c]].c_str();
+		for (int i = b; i < e; ++i) {
+			fprintf(fp, "%s %d %d %d %d %c %c -1 -1 -1 %.17g %.17g ", chr, g.se_start[(size_t)i] + 1, g.se_end[(size_t)i] + 1,
+			        (int)g.se_left_type[(size_t)i], (int)g.se_right_type[(size_t)i], sc[g.se_left_strand[(size_t)i] + 1],
+			        sc[g.se_right_strand[(size_t)i] + 1], g.se_left_cls[(size_t)i], g.se_right_cls[(size_t)i]);
+			fprintf(fp, "%d ", g.prev_off[(size_t)i + 1] - g.prev_off[(size_t)i]);
+			for (int k = g.prev_off[(size_t)i]; k < g.prev_off[(size_t)i + 1]; ++k) fprintf(fp, "%d ", g.se_end[(size_t)(b + g.prev_idx[(size_t)k])] + 1);
+			fprintf(fp, "%d ", g.next_off[(size_t)i + 1] - g.next_off[(size_t)i]);
+			for (int k = g.next_off[(size_t)i]; k < g.next_off[(size_t)i + 1]; ++k) fprintf(fp, "%d ", g.se_start[(size_t)(b + g.next_idx[(size_t)k])] + 1);
+			fprintf(fp, "\n");
+		}
+	}
+	return fclose(fp) == 0;
+}
+
+// -------------------------------------------------------------------------------------------
 // binary cache
 // -------------------------------------------------------------------------------------------
 namespace {

@@ -41,6 +41,13 @@ struct Graph {
 bool load_subexon_graph(const std::string &path, const std::vector<std::string> &chr_names,
                         double classifier_threshold, Graph &g, std::string &err);
 
+// Writes the graph in the combined-subexon text format (/root/reference/CombineSubexons.cpp:1617-1684: `chr start end
+// leftType rightType leftStrand rightStrand -1 -1 -1 leftClassifier rightClassifier prevCnt prev... nextCnt next...`,
+// 1-based coordinates, prev = end coordinate of a predecessor, next = start coordinate of a successor, classifiers
+// with 17 significant digits).  What is written is the graph as stage 3 uses it (after the classifier filter and the
+// fix-ups of the reader); reading the file back gives the same graph.
+bool write_subexon_file(const Graph &g, const std::string &path);
+
 // Binary form of a parsed graph: the arrays above, little-endian, behind a header that pins the source
 // file (size, mtime), the classifier threshold and the chromosome names it was built for.  `load_graph_cache` maps the
 // file and copies the arrays out; it returns false (and leaves `g` untouched) when the file is missing, truncated or

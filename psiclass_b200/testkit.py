@@ -69,6 +69,8 @@ def lib():
         t.tk_total_read_cnt.restype = C.c_double
         t.tk_total_read_cnt.argtypes = [C.c_void_p, C.c_int]
         t.tk_default_cfg.argtypes = [C.POINTER(SynthCfg)]
+        t.tk_graph_roundtrip.argtypes = [C.c_void_p]
+        t.tk_write_subexon_file.argtypes = [C.c_void_p, C.c_char_p]
         _tk = t
     return _tk
 
@@ -132,6 +134,14 @@ class Workload:
         if rc >= 100:
             raise RuntimeError(lib().tk_error(self.h).decode())
         return r
+
+    def write_subexon_file(self, path):
+        if lib().tk_write_subexon_file(self.h, path.encode()):
+            raise RuntimeError("cannot write " + path)
+
+    def graph_roundtrip(self):
+        """0 when writing the graph as text / as the binary cache and reading it back reproduces it"""
+        return lib().tk_graph_roundtrip(self.h)
 
     def close(self):
         if self.h:

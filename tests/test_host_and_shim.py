@@ -181,3 +181,21 @@ def test_graph_cache_round_trip_and_invalidation(tmp_path):
     stamp = os.path.getmtime(cache)
     os.utime(os.path.join(d, "subexon_combined.out"), (1, 1))
     assert classes("g") == ref and os.path.getmtime(cache) != stamp   # reparsed and rewritten for the new stamp
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=41, n_genes=200, n_samples=1, p_overlap=0.2),
+    dict(seed=44, n_genes=150, n_samples=1, p_paralog=0.15, exon_mu=2.4, iso_lambda=4.0, p_alt=0.4, p_ir=0.1),
+    dict(seed=1003, n_genes=3, n_samples=1, dense=1, exon_min=80, exon_max=100),
+])
+def test_subexon_file_writer_and_cache_round_trip(cfg):
+    """the graph written in the combined-subexon text format (CombineSubexons.cpp:1617-1684) and as the
+    binary cache reads back to the same components, gene ids, classifiers and edges."""
+    wl = testkit.Workload.synth(threads=2, mean_pairs=1.0, **cfg)
+    assert wl.graph_roundtrip() == 0
+
+
+@pytest.mark.parametrize("name", ["synth_small", "dp_small", "example"])
+def test_subexon_file_round_trip_on_fixtures(name, tmp_path):
+    wl = testkit.Workload.load(stage_fixture(name, tmp_path))
+    assert wl.graph_roundtrip() == 0

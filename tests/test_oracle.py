@@ -80,3 +80,21 @@ def test_oracle_matches_live_reference(args, tmp_path):
     n = len(open(os.path.join(d, "bamlist")).read().split())
     for s in range(n):
         assert gtf_body(os.path.join(d, "orc_sample_%d.gtf" % s)) == gtf_body(os.path.join(d, "ref_sample_%d.gtf" % s))
+
+
+@pytest.mark.parametrize("name", ["synth_small", "dp_small"])
+def test_reference_reads_the_written_subexon_file(name, tmp_path):
+    """The subexon-file writer (psc::write_subexon_file): the UNMODIFIED reference, run on the file we write from the
+    parsed graph, produces the same tables and GTFs as on the original combined subexon file."""
+    if not os.path.exists(REF_DUMP):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    from psiclass_b200 import testkit
+    d = stage_fixture(name, tmp_path)
+    testkit.Workload.load(d).write_subexon_file(os.path.join(d, "rewritten.out"))
+    out = run([REF_DUMP, "-s", "rewritten.out", "--lb", "bamlist", "-o", "rw"], cwd=d)
+    golden = open(os.path.join(d, "ref_dump.txt")).read()
+    assert dump_lines(out) == dump_lines(golden)
+    assert atcnt_lines(out) == atcnt_lines(golden)
+    n = len(open(os.path.join(d, "bamlist")).read().split())
+    for s in range(n):
+        assert gtf_body(os.path.join(d, "rw_sample_%d.gtf" % s)) == gtf_body(os.path.join(d, "ref_sample_%d.gtf" % s))

@@ -4,6 +4,7 @@
 // GPU box; the CPU shim only in the "not gpu" logic tests), so everything goes through the C ABI.
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstring>
@@ -105,6 +106,39 @@ tk_handle *tk_load(const char *dir)
 	psc::load_subexon_graph(d + "/subexon_combined.out", h->samples[0].chr_names, 0.05, h->g, h->err);
 	return h;
 }
+
+// writes the graph as a combined-subexon text file, reads it back and compares every array; also the binary cache.
+// 0: both round trips reproduce the graph
+int tk_graph_roundtrip(tk_handle *h)
+{
+	char tmpl[] = "/tmp/psc_rt_XXXXXX";
+	int fd = mkstemp(tmpl);
+	if (fd < 0) return 90;
+	close(fd);
+	std::string path = tmpl, err;
+	int rc = 0;
+	auto same = [&](const psc::Graph &a, const psc::Graph &b) {
+		return a.n_comp == b.n_comp && a.comp_off == b.comp_off && a.comp_chr == b.comp_chr && a.comp_start == b.comp_start &&
+		       a.comp_end == b.comp_end && a.comp_base_gene == b.comp_base_gene && a.comp_used_gene == b.comp_used_gene &&
+		       a.se_start == b.se_start && a.se_end == b.se_end && a.se_left_type == b.se_left_type && a.se_right_type == b.se_right_type &&
+		       a.se_left_strand == b.se_left_strand && a.se_right_strand == b.se_right_strand && a.se_left_cls == b.se_left_cls &&
+		       a.se_right_cls == b.se_right_cls && a.se_gene_id == b.se_gene_id && a.next_off == b.next_off && a.next_idx == b.next_idx &&
+		       a.prev_off == b.prev_off && a.prev_idx == b.prev_idx;
+	};
+	psc::Graph g2, g3;
+	if (!psc::write_subexon_file(h->g, path)) rc = 91;
+	else if (!psc::load_subexon_graph(path, h->g.chr_names, 0.05, g2, err)) rc = 92;
+	else if (!same(h->g, g2)) rc = 93;
+	else if (!psc::save_graph_cache(path + ".pscgraph", path, 0.05, g2)) rc = 94;
+	else if (!psc::load_graph_cache(path + ".pscgraph", path, h->g.chr_names, 0.05, g3)) rc = 95;
+	else if (!same(h->g, g3)) rc = 96;
+	else if (psc::load_graph_cache(path + ".pscgraph", path, h->g.chr_names, 0.07, g3)) rc = 97; // other threshold: must be refused
+	remove(path.c_str());
+	remove((path + ".pscgraph").c_str());
+	return rc;
+}
+
+int tk_write_subexon_file(tk_handle *h, const char *path) { return psc::write_subexon_file(h->g, path) ? 0 : 1; }
 
 const char *tk_error(tk_handle *h) { return h->err.c_str(); }
 void tk_free(tk_handle *h) { delete h; }
