@@ -1,6 +1,7 @@
 #include "vote.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cstdlib>
 #include <cstring>
 
@@ -69,24 +70,29 @@ void vote_core(std::vector<VoteTx> &txs, int sampleCnt, double minAvgDepth, FILE
 	}
 }
 
-// Vote.cpp:31-58
-static void gtf_field(char *s, const char *field, char *ret)
+// The attribute parser of Vote.cpp:31-58, restated: the value of `field "<value>";` is the whitespace-delimited token that
+// starts two characters after the first blank following the field name, cut at its last double quote.
+static std::string gtf_value(const std::string &line, const char *field)
 {
-	char *p = strstr(s, field);
-	if (p == NULL) return;
-	for (; *p != ' '; ++p)
-		;
-	p += 2;
-	sscanf(p, "%s", ret);
-	p = ret + strlen(ret);
-	while (*p != '\"') --p;
-	*p = '\0';
+	size_t at = line.find(field);
+	if (at == std::string::npos) return std::string();
+	size_t blank = line.find(' ', at);
+	if (blank == std::string::npos || blank + 2 > line.size()) return std::string();
+	size_t from = blank + 2, to = from;
+	while (to < line.size() && !isspace((unsigned char)line[to])) ++to;
+	std::string tok = line.substr(from, to - from);
+	size_t quote = tok.rfind('"');
+	if (quote != std::string::npos) tok.erase(quote);
+	return tok;
 }
-static int tail_number(const char *s)
+// the decimal number an id such as "chr2.17.3" ends with (Vote.cpp:47-58)
+static int trailing_number(const std::string &id)
 {
-	int len = (int)strlen(s), ret = 0, factor = 1;
-	for (int i = len - 1; i >= 0 && s[i] >= '0' && s[i] <= '9'; --i, factor *= 10) ret += factor * (s[i] - '0');
-	return ret;
+	size_t b = id.size();
+	while (b > 0 && id[b - 1] >= '0' && id[b - 1] <= '9') --b;
+	long long v = 0;
+	for (size_t k = b; k < id.size(); ++k) v = v * 10 + (id[k] - '0');
+	return (int)v;
 }
 
 bool vote_read_gtfs(const std::string &listPath, std::vector<VoteTx> &txs, int &sampleCnt, std::string &err)
@@ -125,17 +131,13 @@ bool vote_read_gtfs(const std::string &listPath, std::vector<VoteTx> &txs, int &
 				flush();
 				continue;
 			}
+			const std::string text = line;
 			cur.chrom = chrom;
-			gtf_field(line, "gene_id", buffer);
-			cur.gene_id = tail_number(buffer);
-			gtf_field(line, "transcript_id", buffer);
-			cur.transcript_id = tail_number(buffer);
-			gtf_field(line, "FPKM", buffer);
-			cur.fpkm = atof(buffer);
-			gtf_field(line, "TPM", buffer);
-			cur.tpm = atof(buffer);
-			gtf_field(line, "cov", buffer);
-			cur.cov = atof(buffer);
+			cur.gene_id = trailing_number(gtf_value(text, "gene_id"));
+			cur.transcript_id = trailing_number(gtf_value(text, "transcript_id"));
+			cur.fpkm = atof(gtf_value(text, "FPKM").c_str());
+			cur.tpm = atof(gtf_value(text, "TPM").c_str());
+			cur.cov = atof(gtf_value(text, "cov").c_str());
 			cur.strand = strand[0];
 			cur.exons.push_back({start, end});
 			have = true;
