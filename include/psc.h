@@ -114,7 +114,9 @@ const char *psc_last_error(const psc_ctx *ctx);
 
 int psc_set_params(psc_ctx *ctx, const psc_params *p);
 int psc_set_graph(psc_ctx *ctx, const psc_graph *g);
-/* Copies the sample's reads host->device (asynchronously, on the context's stream). */
+/* Copies the sample's reads host->device: the copies are only ENQUEUED on the context's stream, so the caller's arrays
+ * must stay valid and unchanged until the next synchronising call on the context (psc_build_constraints).  Pinned arrays
+ * upload at full PCIe speed.  Replaces the per-sample Alignments stream of classes.cpp:264-283. */
 int psc_set_reads(psc_ctx *ctx, int32_t sample, const psc_reads *r);
 
 /* Alignment -> constraint tables for every (sample, component). */
@@ -140,7 +142,8 @@ typedef struct psc_timing {
 	/* per-kernel device time (CUDA events around every launch, summed) and launch counts of the last
 	 * psc_build_constraints + psc_solve: 0 group_ranges, 1 build_constraints, 2 prologue,
 	 * 3 enumerate, 4 dp_units, 5 units phase 1 (pick round 1), 6 emit, 7 dp_merge,
-	 * 8 units phase 2 (pick round 2, refine, EM), 9 units phase 3 (rescue), 10 dp2_units (static-program DP) */
+	 * 8 units phase 2 (pick round 2, refine, EM), 9 units phase 3 (rescue), 10 dp2_units (static-program DP),
+	 * 11 dp2_units launched one thread per unit (experiment switch PSC_DP_T1_FRAC, off by default) */
 	double kernel_ms[12];
 	int64_t kernel_count[12];
 	int64_t kernel_bytes[12]; /* algorithmic bytes attributed to the kernel, 0 if not modelled */
