@@ -96,3 +96,19 @@ def test_psiclass_driver_with_drop_in_on_cpu_shim(tmp_path):
 @pytest.mark.gpu
 def test_psiclass_driver_with_drop_in_cuda(tmp_path):
     _driver_run(os.path.join(BIN, "classes"), tmp_path)
+
+
+def test_perf_json_and_vote_depth_on_cpu_shim(tmp_path):
+    """`PSC_PERF_JSON` (what bench.py reads) is valid JSON with the phase times and one entry per shard; `--vote-depth`
+    is vote-transcripts' -d."""
+    import json
+    d = stage_fixture("dp_small", tmp_path)
+    env = dict(os.environ, PSC_GPUS="2", PSC_PERF_JSON=os.path.join(d, "perf.json"))
+    run([os.path.join(SHIM, "classes_shim"), "--lb", "bamlist", "-s", "subexon_combined.out", "-o", "new", "-p", "3",
+         "--vote", "v.gtf", "--vote-depth", "0.2"], cwd=d, env=env)
+    perf = json.load(open(os.path.join(d, "perf.json")))
+    assert perf["gpus"] == 2 and len(perf["shards"]) == 2 and perf["samples"] == 3
+    assert sum(s["components"] for s in perf["shards"]) == perf["components"]
+    for k in ("decode_s", "graph_s", "device_s", "gtf_s", "vote_s", "total_s", "decode_MBps", "bam_bytes", "reads"):
+        assert k in perf
+    assert open(os.path.join(d, "v.gtf")).read() == run([os.path.join(BIN, "vote-transcripts"), "--lg", gtf_list(d, "new"), "-d", "0.2"])
