@@ -3,6 +3,7 @@
 // Alignments::GetGeneralInfo (alignments.hpp:489-571).
 #include "bam_io.h"
 
+#include <sys/mman.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -453,8 +454,28 @@ bool decode_bam(const std::string &path, int threads, SampleReads &out, std::str
 	uint64_t total = 0;
 	if (!index_blocks(f, blocks, total, err))
 		return false;
-	std::unique_ptr<uint8_t[]> image(new uint8_t[total + 8]); // not zero-filled: every byte is written by the inflate
-	const size_t CHUNK = 64;                                  // blocks per unit of work (~4 MB inflated)
+	// The inflated image is an anonymous mapping: pages the parser is done with are handed back (MADV_DONTNEED) and the
+	// inflate workers stay at most WINDOW chunks ahead of it, so a sample holds ~0.4 GB of inflated data at a time
+	// instead of all of it (2.8 GB per sample on the bench workload).
+	struct Mapping {
+		uint8_t *p = nullptr;
+		size_t n = 0;
+		~Mapping() { if (p) munmap(p, n); }
+		uint8_t *get() const { return p; }
+	} image;
+	image.n = (size_t)total + 4096;
+	{
+		void *m = mmap(nullptr, image.n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+		if (m == MAP_FAILED) {
+			err = "out of memory for the inflated BAM image";
+			return false;
+		}
+		image.p = (uint8_t *)m;
+	}
+	const size_t CHUNK = 64;   // blocks per unit of work (~4 MB inflated)
+	const size_t WINDOW = 96;  // chunks the inflate may run ahead of the parser
+	std::atomic<size_t> consumedChunk(0);
+	std::atomic<bool> stop(false);
 	const size_t nChunks = (blocks.size() + CHUNK - 1) / CHUNK;
 	std::unique_ptr<std::atomic<unsigned char>[]> chunkDone(new std::atomic<unsigned char>[nChunks + 1]);
 	for (size_t k = 0; k <= nChunks; ++k) chunkDone[k].store(0, std::memory_order_relaxed);
@@ -467,6 +488,9 @@ bool decode_bam(const std::string &path, int threads, SampleReads &out, std::str
 		for (;;) {
 			size_t k = next.fetch_add(1);
 			if (k >= nChunks) break;
+			while (k >= consumedChunk.load(std::memory_order_acquire) + WINDOW && !stop.load(std::memory_order_relaxed))
+				std::this_thread::sleep_for(std::chrono::microseconds(50));
+			if (stop.load(std::memory_order_relaxed)) break;
 			size_t i = k * CHUNK, e = std::min(blocks.size(), i + CHUNK);
 			for (; i < e && init; ++i) {
 				const Block &b = blocks[i];
@@ -488,8 +512,29 @@ bool decode_bam(const std::string &path, int threads, SampleReads &out, std::str
 	for (int t = 0; t < std::max(1, threads); ++t) pool.emplace_back(work);
 	struct Joiner {
 		std::vector<std::thread> &p;
-		~Joiner() { for (auto &t : p) if (t.joinable()) t.join(); }
-	} joiner{pool};
+		std::atomic<bool> &stop;
+		~Joiner()
+		{
+			stop.store(true); // an early return must not leave workers waiting for the parser
+			for (auto &t : p) if (t.joinable()) t.join();
+		}
+	} joiner{pool, stop};
+	// chunks [0, relChunk) lie entirely behind the parser; their pages up to releasedUpTo have been handed back
+	size_t relChunk = 0, releasedUpTo = 0;
+	auto release_behind = [&](size_t off) {
+		while (relChunk < nChunks) {
+			size_t b = std::min(blocks.size(), (relChunk + 1) * CHUNK);
+			uint64_t chunkEnd = b < blocks.size() ? blocks[b].uoff : total;
+			if (chunkEnd > off) break;
+			++relChunk;
+			size_t lim = (size_t)chunkEnd & ~(size_t)4095;
+			if (lim > releasedUpTo) {
+				madvise(image.get() + releasedUpTo, lim - releasedUpTo, MADV_DONTNEED);
+				releasedUpTo = lim;
+			}
+			consumedChunk.store(relChunk, std::memory_order_release);
+		}
+	};
 	// bytes [0, ready) of the image are final
 	size_t frontChunk = 0;
 	uint64_t ready = 0;
@@ -539,6 +584,7 @@ bool decode_bam(const std::string &path, int threads, SampleReads &out, std::str
 	size_t n = usize;
 	std::vector<uint32_t> cigbuf;
 	while (off + 4 <= n) {
+		release_behind(off);
 		if (!wait_for(off + 4)) break;
 		uint32_t bs = rd32(base + off);
 		if (off + 4 + (size_t)bs <= n && !wait_for(off + 4 + (size_t)bs)) break;
@@ -568,6 +614,7 @@ bool decode_bam(const std::string &path, int threads, SampleReads &out, std::str
 		        t != NULL, t ? aux_int(t) : 1);
 	}
 	acc.finish();
+	consumedChunk.store(nChunks, std::memory_order_release); // a trailing block without records: let the workers finish
 	for (auto &t : pool) t.join();
 	if (!ok) {
 		err = "BGZF inflate failed";
