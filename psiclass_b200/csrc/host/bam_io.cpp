@@ -3,7 +3,10 @@
 // Alignments::GetGeneralInfo (alignments.hpp:489-571).
 #include "bam_io.h"
 
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -41,6 +44,49 @@ struct Block {
 	uint64_t uoff; // offset in the inflated image
 };
 
+// read-only view of a whole file: mapped (no copy; the page cache is the buffer), or read if it cannot be mapped
+struct FileView {
+	const uint8_t *p = nullptr;
+	size_t n = 0;
+	bool mapped = false;
+	std::vector<uint8_t> owned;
+	~FileView()
+	{
+		if (mapped && p) munmap(const_cast<uint8_t *>(p), n);
+	}
+	const uint8_t *data() const { return p; }
+	size_t size() const { return n; }
+	uint8_t operator[](size_t i) const { return p[i]; }
+};
+
+bool load_file(const std::string &path, std::vector<uint8_t> &buf, std::string &err);
+
+bool open_view(const std::string &path, FileView &v, std::string &err)
+{
+	int fd = open(path.c_str(), O_RDONLY);
+	if (fd < 0) {
+		err = "Can not open " + path + ".";
+		return false;
+	}
+	struct stat st;
+	if (fstat(fd, &st) == 0 && st.st_size > 0) {
+		void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+		if (m != MAP_FAILED) {
+			madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+			v.p = (const uint8_t *)m;
+			v.n = (size_t)st.st_size;
+			v.mapped = true;
+			close(fd);
+			return true;
+		}
+	}
+	close(fd);
+	if (!load_file(path, v.owned, err)) return false;
+	v.p = v.owned.data();
+	v.n = v.owned.size();
+	return true;
+}
+
 bool load_file(const std::string &path, std::vector<uint8_t> &buf, std::string &err)
 {
 	FILE *fp = fopen(path.c_str(), "rb");
@@ -67,7 +113,7 @@ inline uint32_t rd32(const uint8_t *p)
 	return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
-bool index_blocks(const std::vector<uint8_t> &f, std::vector<Block> &blocks, uint64_t &total,
+template <class Bytes> bool index_blocks(const Bytes &f, std::vector<Block> &blocks, uint64_t &total,
                   std::string &err, size_t max_blocks = (size_t)-1)
 {
 	size_t off = 0;
@@ -120,7 +166,7 @@ bool inflate_block(const uint8_t *src, uint32_t clen, uint8_t *dst, uint32_t isi
 	return rc == Z_STREAM_END && zs.avail_out == 0;
 }
 
-bool inflate_all(const std::vector<uint8_t> &f, const std::vector<Block> &blocks, uint64_t total,
+template <class Bytes> bool inflate_all(const Bytes &f, const std::vector<Block> &blocks, uint64_t total,
                  int threads, std::vector<uint8_t> &out, std::string &err)
 {
 	out.resize(total);
@@ -231,13 +277,13 @@ bool parse_header(const uint8_t *u, size_t n, size_t &off, std::vector<std::stri
 bool read_bam_header(const std::string &path, std::vector<std::string> &names,
                      std::vector<int32_t> &lens, std::string &err)
 {
-	std::vector<uint8_t> f;
-	if (!load_file(path, f, err))
+	FileView f;
+	if (!open_view(path, f, err))
 		return false;
-	// the header may span several blocks; inflate progressively
+	// the header may span several blocks; inflate progressively (only the first blocks are indexed)
 	std::vector<Block> blocks;
 	uint64_t total = 0;
-	if (!index_blocks(f, blocks, total, err))
+	if (!index_blocks(f, blocks, total, err, 4096))
 		return false;
 	std::vector<uint8_t> u;
 	size_t used = 0;
@@ -447,8 +493,8 @@ void ReadAccumulator::finish()
 // inflate, which is most of the time, does not).
 bool decode_bam(const std::string &path, int threads, SampleReads &out, std::string &err)
 {
-	std::vector<uint8_t> f;
-	if (!load_file(path, f, err))
+	FileView f;
+	if (!open_view(path, f, err))
 		return false;
 	std::vector<Block> blocks;
 	uint64_t total = 0;
